@@ -1,0 +1,510 @@
+// Kernel family 4: graph-regularised non-negative block-coordinate descent (Jacobi over
+// spots, Gauss-Seidel over cell types inside a spot), objective and proportion output.
+//
+// Reference semantics (upstream file:line):
+//   core/solver.py:149-184  per spot: neighbour sum over beta_in (Jacobi), cyclic CD, max-norm stats
+//   core/solver.py:72-99    r = G b; for k: part = Xty_k - r_k + G_kk b_k (+ lam * nsum_k if deg > 0);
+//                           b_k <- max(0, soft(part, rho) / (G_kk + lam*deg)) (0 if denom <= 1e-10);
+//                           r += (b_k_new - b_k) * G[:, k] when the step is non-zero
+//   core/solver.py:395-413  rel = max|delta| / (max|old| + 1e-10); stop when rel < tol
+//   core/solver.py:269-284  objective;  core/solver.py:445-452 normalisation
+//
+// Sweep kernel mapping (HBM-bound: (12*Kp + 4*deg + 4) bytes per spot per sweep):
+//   CTA = 4 independent warps, each owning 32 consecutive spots (tile order, so neighbours are
+//   nearby in memory).
+//   phase A (coalesced): groups of Kp/4 lanes stream whole 16B-aligned rows -- the spot's H row,
+//     its beta row and its neighbours' beta rows -- and leave c = H + lam * nsum and beta_old in
+//     shared memory.
+//   phase B (thread per spot): the K-step coordinate descent is strictly sequential per spot, so
+//     each lane runs one spot with the maintained product r[Kp] in registers; the Gram matrix is
+//     a by-value kernel parameter, i.e. every FFMA takes its G operand straight from the constant
+//     bank.  Rank-1 updates are skipped warp-uniformly when no lane moved (most coordinates sit
+//     at the non-negativity bound).
+//   phase C (coalesced): the warp streams its 32 new rows back out.
+//   Convergence statistics: redux.sync max per warp, one atomicMax per CTA, last CTA finalises.
+#include <algorithm>
+#include "fdb_common.cuh"
+
+extern "C" __attribute__((visibility("default"))) int fdb_bcd_init(float *beta, int64_t n_rows, int32_t n_types, void *state, void *stream);
+
+namespace fdb {
+
+struct SolveState {                 // mirrors the 64-byte block documented in fdb200.h
+    unsigned max_diff_bits;
+    unsigned max_abs_bits;
+    unsigned arrived;
+    int sweeps;
+    int converged;
+    float rel_change;
+    float last_max_diff;
+    float last_max_abs;
+    int pad[8];
+};
+static_assert(sizeof(SolveState) == 64, "state block is 64 bytes");
+
+template <int KP>
+struct GramArg {
+    float g[KP * KP];               // g[k * KP + a] = G[a][k] (symmetric), zero padded
+};
+
+__device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+__device__ __forceinline__ void add4(float4 &a, const float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+__device__ __forceinline__ float elem(const float4 &v, int j) { return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w; }
+__device__ __forceinline__ void set_elem(float4 &v, int j, float x)
+{
+    if (j == 0) v.x = x; else if (j == 1) v.y = x; else if (j == 2) v.z = x; else v.w = x;
+}
+
+__device__ __forceinline__ void finalize_state(SolveState *st, float tol)
+{
+    const float md = __uint_as_float(st->max_diff_bits), ma = __uint_as_float(st->max_abs_bits);
+    const float rel = md / (ma + 1e-10f);
+    st->rel_change = rel;
+    st->last_max_diff = md;
+    st->last_max_abs = ma;
+    st->sweeps += 1;
+    if (rel < tol) st->converged = 1;
+    st->max_diff_bits = 0u;
+    st->max_abs_bits = 0u;
+    st->arrived = 0u;
+}
+
+constexpr int kSweepThreads = 128;
+constexpr int kNbrUnroll = 8;
+
+template <int KP>
+__global__ void __launch_bounds__(kSweepThreads)
+bcd_sweep_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP> G,
+                 const float *__restrict__ beta_in, float *__restrict__ beta_out,
+                 const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                 int n_rows, float lam, float rho, float tol, int finalize, SolveState *state)
+{
+    if (*reinterpret_cast<volatile int *>(&state->converged)) return;
+
+    constexpr int Q = KP / 4;                           // float4 chunks per row
+    constexpr int S = (Q % 2 == 1) ? KP : KP + 4;       // smem row stride: odd chunk count => conflict-free 128-bit rows
+    constexpr int SLOTS = 32 / Q;                       // rows streamed per warp instruction
+    constexpr int ITERS = (32 + SLOTS - 1) / SLOTS;
+    extern __shared__ __align__(16) float sweep_smem[];
+    float *c_tile = sweep_smem;
+    float *b_tile = sweep_smem + kSweepThreads * S;
+    int *deg_tile = reinterpret_cast<int *>(sweep_smem + 2 * kSweepThreads * S);
+    __shared__ unsigned red[2][kSweepThreads / 32];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wbase = blockIdx.x * kSweepThreads + warp * 32;
+    float *cw = c_tile + warp * 32 * S;
+    float *bw = b_tile + warp * 32 * S;
+    int *dw = deg_tile + warp * 32;
+
+    // ---------------- phase A: stream rows, build c = H + lam * sum_j beta_old[j]
+    {
+        const int slot = lane / Q, q = lane - slot * Q;
+#pragma unroll 1
+        for (int it = 0; it < ITERS; ++it) {
+            const int lr = it * SLOTS + slot;
+            const int p = wbase + lr;
+            if (slot < SLOTS && lr < 32) {
+                float4 own = make_float4(0.f, 0.f, 0.f, 0.f), cc = own;
+                int deg = 0;
+                if (p < n_rows) {
+                    const int s = __ldg(indptr + p), e = __ldg(indptr + p + 1);
+                    deg = e - s;
+                    own = ld4(beta_in + (size_t)p * KP + 4 * q);
+                    cc = __ldcs(reinterpret_cast<const float4 *>(h + (size_t)p * KP + 4 * q));
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int j0 = s; j0 < e; j0 += kNbrUnroll) {
+                        int nb[kNbrUnroll];
+#pragma unroll
+                        for (int u = 0; u < kNbrUnroll; ++u) nb[u] = j0 + u < e ? __ldg(indices + j0 + u) : -1;
+                        float4 v[kNbrUnroll];
+#pragma unroll
+                        for (int u = 0; u < kNbrUnroll; ++u)
+                            v[u] = nb[u] >= 0 ? ld4(beta_in + (size_t)nb[u] * KP + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int u = 0; u < kNbrUnroll; ++u) add4(acc, v[u]);
+                    }
+                    if (deg > 0) {
+                        cc.x = fmaf(lam, acc.x, cc.x); cc.y = fmaf(lam, acc.y, cc.y);
+                        cc.z = fmaf(lam, acc.z, cc.z); cc.w = fmaf(lam, acc.w, cc.w);
+                    }
+                }
+                st4(cw + lr * S + 4 * q, cc);
+                st4(bw + lr * S + 4 * q, own);
+                if (q == 0) dw[lr] = deg;
+            }
+        }
+    }
+    __syncwarp();
+
+    // ---------------- phase B: one spot per lane, cyclic coordinate descent
+    float dmax = 0.f, amax = 0.f;
+    {
+        const float lam_deg = lam * (float)dw[lane];
+        float r[KP];
+#pragma unroll
+        for (int a = 0; a < KP; ++a) r[a] = 0.f;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const float4 b4 = ld4(bw + lane * S + 4 * q);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = 4 * q + j;
+                const float bk = elem(b4, j);
+                if (__any_sync(kFull, bk != 0.f)) {
+#pragma unroll
+                    for (int a = 0; a < KP; ++a) r[a] = fmaf(bk, G.g[k * KP + a], r[a]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const float4 b4 = ld4(bw + lane * S + 4 * q);
+            const float4 c4 = ld4(cw + lane * S + 4 * q);
+            float4 n4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = 4 * q + j;
+                const float old = elem(b4, j);
+                const float gkk = G.g[k * KP + k];
+                const float part = elem(c4, j) - r[k] + gkk * old;
+                const float den = gkk + lam_deg;
+                float nv = 0.f;
+                if (den > 1e-10f) {
+                    const float sh = part > rho ? part - rho : (part < -rho ? part + rho : 0.f);
+                    nv = fmaxf(0.f, sh / den);
+                }
+                const float delta = nv - old;
+                if (__any_sync(kFull, delta != 0.f)) {
+#pragma unroll
+                    for (int a = 0; a < KP; ++a) r[a] = fmaf(delta, G.g[k * KP + a], r[a]);
+                }
+                dmax = fmaxf(dmax, fabsf(delta));
+                amax = fmaxf(amax, fabsf(old));
+                set_elem(n4, j, nv);
+            }
+            st4(bw + lane * S + 4 * q, n4);
+        }
+        if (wbase + lane >= n_rows) { dmax = 0.f; amax = 0.f; }
+    }
+    __syncwarp();
+
+    // ---------------- phase C: stream the warp's new rows out
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        const int idx = lane + 32 * i;
+        const int lr = idx / Q, q = idx - lr * Q;
+        if (wbase + lr < n_rows) st4(beta_out + (size_t)(wbase + lr) * KP + 4 * q, ld4(bw + lr * S + 4 * q));
+    }
+
+    // ---------------- convergence statistics
+    const unsigned wd = __reduce_max_sync(kFull, __float_as_uint(dmax));
+    const unsigned wa = __reduce_max_sync(kFull, __float_as_uint(amax));
+    if (lane == 0) { red[0][warp] = wd; red[1][warp] = wa; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned bd = 0u, ba = 0u;
+#pragma unroll
+        for (int w = 0; w < kSweepThreads / 32; ++w) { bd = max(bd, red[0][w]); ba = max(ba, red[1][w]); }
+        if (bd > *reinterpret_cast<volatile unsigned *>(&state->max_diff_bits)) atomicMax(&state->max_diff_bits, bd);
+        if (ba > *reinterpret_cast<volatile unsigned *>(&state->max_abs_bits)) atomicMax(&state->max_abs_bits, ba);
+        if (finalize) {
+            __threadfence();
+            if (atomicAdd(&state->arrived, 1u) == gridDim.x - 1) {
+                __threadfence();
+                finalize_state(state, tol);
+            }
+        }
+    }
+}
+
+__global__ void bcd_finalize_kernel(SolveState *state, float tol)
+{
+    if (state->converged) return;
+    finalize_state(state, tol);
+}
+
+__global__ void __launch_bounds__(256)
+bcd_init_kernel(float *__restrict__ beta, int64_t n_rows, int kp, int n_types, SolveState *state)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && state) {
+        SolveState z = {};
+        *state = z;
+    }
+    if (i >= n_rows * kp) return;
+    const int k = (int)(i % kp);
+    beta[i] = k < n_types ? 1.0f / (float)n_types : 0.f;
+}
+
+template <int KP>
+static int launch_sweep(const float *h, const float *host_gram, int n_types, const float *beta_in,
+                        float *beta_out, const int32_t *indptr, const int32_t *indices, int64_t n_rows,
+                        float lam, float rho, float tol, int finalize, SolveState *state, cudaStream_t st)
+{
+    GramArg<KP> G;
+    for (int i = 0; i < KP * KP; ++i) G.g[i] = 0.f;
+    for (int k = 0; k < n_types; ++k)
+        for (int a = 0; a < n_types; ++a) G.g[k * KP + a] = host_gram[a * n_types + k];
+    const int grid = (int)ceil_div(n_rows, kSweepThreads);
+    constexpr int S = ((KP / 4) % 2 == 1) ? KP : KP + 4;
+    constexpr size_t smem = (size_t)kSweepThreads * (2 * S + 1) * 4;
+    static bool configured = false;              // per instantiation
+    if (!configured) {
+        FDB_CUDA(cudaFuncSetAttribute(bcd_sweep_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    bcd_sweep_kernel<KP><<<grid, kSweepThreads, smem, st>>>(h, G, beta_in, beta_out, indptr, indices, (int)n_rows,
+                                                         lam, rho, tol, finalize, state);
+    FDB_LAUNCH_CHECK("bcd_sweep_kernel");
+    return FDB_OK;
+}
+
+static int dispatch_sweep(const float *h, const float *host_gram, int n_types, const float *beta_in,
+                          float *beta_out, const int32_t *indptr, const int32_t *indices, int64_t n_rows,
+                          float lam, float rho, float tol, int finalize, SolveState *state, cudaStream_t st)
+{
+#define FDB_SWEEP_CASE(KP_)                                                                            \
+    case KP_:                                                                                          \
+        return launch_sweep<KP_>(h, host_gram, n_types, beta_in, beta_out, indptr, indices, n_rows,    \
+                                 lam, rho, tol, finalize, state, st);
+    switch (fdb_padded_types(n_types)) {
+        FDB_SWEEP_CASE(4) FDB_SWEEP_CASE(8) FDB_SWEEP_CASE(12) FDB_SWEEP_CASE(16)
+        FDB_SWEEP_CASE(20) FDB_SWEEP_CASE(24) FDB_SWEEP_CASE(28) FDB_SWEEP_CASE(32)
+        FDB_SWEEP_CASE(36) FDB_SWEEP_CASE(40) FDB_SWEEP_CASE(44) FDB_SWEEP_CASE(48)
+        FDB_SWEEP_CASE(52) FDB_SWEEP_CASE(56) FDB_SWEEP_CASE(60) FDB_SWEEP_CASE(64)
+    default:
+        set_error("n_types must be in [1, %d], got %d", FDB_MAX_TYPES, n_types);
+        return FDB_ERR_UNSUPPORTED;
+    }
+#undef FDB_SWEEP_CASE
+}
+
+// ------------------------------------------------------------------------------------
+// objective terms (float64 accumulation), warp per spot
+// ------------------------------------------------------------------------------------
+template <int NK>
+__global__ void __launch_bounds__(256)
+objective_kernel(const float *__restrict__ beta, const float *__restrict__ h, const float *__restrict__ ysq,
+                 const float *__restrict__ gram_padded, const int32_t *__restrict__ indptr,
+                 const int32_t *__restrict__ indices, int64_t n_rows, int kp, double *__restrict__ out)
+{
+    extern __shared__ float gs[];                          // kp x kp
+    for (int i = threadIdx.x; i < kp * kp; i += blockDim.x) gs[i] = gram_padded[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double cross = 0.0, quad = 0.0, lap = 0.0, l1 = 0.0, yy = 0.0;
+    const bool on0 = lane < kp, on1 = NK == 2 && lane + 32 < kp;
+    for (int64_t p = warp_global; p < n_rows; p += n_warps) {
+        const float b0 = on0 ? beta[p * kp + lane] : 0.f;
+        const float b1 = on1 ? beta[p * kp + 32 + lane] : 0.f;
+        const float h0 = on0 ? h[p * kp + lane] : 0.f;
+        const float h1 = on1 ? h[p * kp + 32 + lane] : 0.f;
+        float gb0 = 0.f, gb1 = 0.f;
+        unsigned m = __ballot_sync(kFull, b0 != 0.f);
+        while (m) {
+            const int c = __ffs(m) - 1;
+            m &= m - 1;
+            const float bc = __shfl_sync(kFull, b0, c);
+            if (on0) gb0 = fmaf(gs[c * kp + lane], bc, gb0);
+            if (on1) gb1 = fmaf(gs[c * kp + 32 + lane], bc, gb1);
+        }
+        if (NK == 2) {
+            m = __ballot_sync(kFull, b1 != 0.f);
+            while (m) {
+                const int c = __ffs(m) - 1;
+                m &= m - 1;
+                const float bc = __shfl_sync(kFull, b1, c);
+                if (on0) gb0 = fmaf(gs[(c + 32) * kp + lane], bc, gb0);
+                if (on1) gb1 = fmaf(gs[(c + 32) * kp + 32 + lane], bc, gb1);
+            }
+        }
+        const int s = indptr[p], e = indptr[p + 1];
+        float n0 = 0.f, n1 = 0.f;
+        for (int j = s; j < e; ++j) {
+            const int64_t nb = indices[j];
+            if (on0) n0 += beta[nb * kp + lane];
+            if (on1) n1 += beta[nb * kp + 32 + lane];
+        }
+        const float deg = (float)(e - s);
+        cross += (double)(b0 * h0) + (double)(b1 * h1);
+        quad += (double)(b0 * gb0) + (double)(b1 * gb1);
+        lap += (double)b0 * (double)(deg * b0 - n0) + (double)b1 * (double)(deg * b1 - n1);
+        l1 += (double)fabsf(b0) + (double)fabsf(b1);
+        if (lane == 0) yy += (double)ysq[p];
+    }
+    __shared__ double red[5][8];
+    cross = warp_sum(cross); quad = warp_sum(quad); lap = warp_sum(lap); l1 = warp_sum(l1); yy = warp_sum(yy);
+    const int warp = threadIdx.x >> 5;
+    if (lane == 0) { red[0][warp] = cross; red[1][warp] = quad; red[2][warp] = lap; red[3][warp] = l1; red[4][warp] = yy; }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
+        atomicAdd(out + threadIdx.x, t);
+    }
+}
+
+__global__ void pad_gram_kernel(const float *__restrict__ src, int n_types, int kp, float *__restrict__ dst)
+{
+    for (int i = threadIdx.x; i < kp * kp; i += blockDim.x) {
+        const int a = i / kp, c = i - a * kp;
+        dst[i] = (a < n_types && c < n_types) ? src[a * n_types + c] : 0.f;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// un-permute + widen + normalise, warp per spot
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+finish_kernel(const float *__restrict__ beta, const int32_t *__restrict__ order, int64_t n_rows, int kp,
+              int n_types, double *__restrict__ beta_out, double *__restrict__ prop_out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t p = warp_global; p < n_rows; p += n_warps) {
+        const double b0 = lane < n_types ? (double)beta[p * kp + lane] : 0.0;
+        const double b1 = lane + 32 < n_types ? (double)beta[p * kp + 32 + lane] : 0.0;
+        const double tot = warp_sum(b0 + b1);
+        const int64_t o = order ? (int64_t)order[p] : p;
+        const double den = tot > 1e-10 ? tot : 1e-10;
+        const double uni = 1.0 / (double)n_types;
+        if (lane < n_types) {
+            if (beta_out) beta_out[o * n_types + lane] = b0;
+            if (prop_out) prop_out[o * n_types + lane] = tot == 0.0 ? uni : b0 / den;
+        }
+        if (lane + 32 < n_types) {
+            if (beta_out) beta_out[o * n_types + 32 + lane] = b1;
+            if (prop_out) prop_out[o * n_types + 32 + lane] = tot == 0.0 ? uni : b1 / den;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+rows_gather_kernel(const float *__restrict__ src, const int32_t *__restrict__ rows, int64_t n_list,
+                   int chunks, float *__restrict__ dst)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_list * chunks) return;
+    const int64_t i = t / chunks;
+    const int q = (int)(t - i * chunks);
+    st4(dst + (i * chunks + q) * 4, ld4(src + ((int64_t)rows[i] * chunks + q) * 4));
+}
+
+}  // namespace fdb
+
+using namespace fdb;
+
+static int check_solver_args(const void *h, const void *gram, const void *a, const void *b, const void *ptr,
+                             int64_t n_rows, int n_types, const void *state)
+{
+    FDB_REQUIRE(n_rows >= 0 && n_rows < ((int64_t)1 << 31) - 256, "n_rows out of range");
+    FDB_REQUIRE(n_types >= 1 && n_types <= FDB_MAX_TYPES, "n_types must be in [1, %d], got %d", FDB_MAX_TYPES, n_types);
+    FDB_REQUIRE(n_rows == 0 || (h && gram && a && b && ptr && state), "null pointer");
+    return FDB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fdb_bcd_sweep(const float *h, const float *host_gram, const float *beta_in, float *beta_out,
+                             const int32_t *indptr, const int32_t *indices, int64_t n_rows, int32_t n_types,
+                             float lambda, float rho_scaled, float tol, int32_t finalize, void *state,
+                             void *stream)
+{
+    int rc = check_solver_args(h, host_gram, beta_in, beta_out, indptr, n_rows, n_types, state);
+    if (rc || n_rows == 0) return rc;
+    return dispatch_sweep(h, host_gram, n_types, beta_in, beta_out, indptr, indices, n_rows, lambda, rho_scaled,
+                          tol, finalize, (SolveState *)state, (cudaStream_t)stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int fdb_bcd_finalize(void *state, float tol, void *stream)
+{
+    FDB_REQUIRE(state != nullptr, "null state");
+    bcd_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((SolveState *)state, tol);
+    FDB_LAUNCH_CHECK("bcd_finalize_kernel");
+    return FDB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fdb_bcd_init(float *beta, int64_t n_rows, int32_t n_types, void *state, void *stream)
+{
+    FDB_REQUIRE(n_rows >= 0 && n_types >= 1, "bad shape");
+    const int kp = fdb_padded_types(n_types);
+    const int64_t total = n_rows * kp;
+    bcd_init_kernel<<<(int)std::max<int64_t>(1, ceil_div(total, 256)), 256, 0, (cudaStream_t)stream>>>(
+        beta, n_rows, kp, n_types, (SolveState *)state);
+    FDB_LAUNCH_CHECK("bcd_init_kernel");
+    return FDB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fdb_bcd_solve(const float *h, const float *host_gram, float *beta_a, float *beta_b,
+                             const int32_t *indptr, const int32_t *indices, int64_t n_rows, int32_t n_types,
+                             float lambda, float rho_scaled, int32_t max_iter, float tol, void *state,
+                             void *stream)
+{
+    int rc = check_solver_args(h, host_gram, beta_a, beta_b, indptr, n_rows, n_types, state);
+    if (rc) return rc;
+    FDB_REQUIRE(max_iter >= 0, "max_iter must be non-negative, got %d", max_iter);
+    rc = fdb_bcd_init(beta_a, n_rows, n_types, state, stream);
+    if (rc || n_rows == 0) return rc;
+    float *cur = beta_a, *nxt = beta_b;
+    for (int it = 0; it < max_iter; ++it) {
+        rc = dispatch_sweep(h, host_gram, n_types, cur, nxt, indptr, indices, n_rows, lambda, rho_scaled, tol, 1,
+                            (SolveState *)state, (cudaStream_t)stream);
+        if (rc) return rc;
+        float *t = cur; cur = nxt; nxt = t;
+    }
+    return FDB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fdb_objective_terms(const float *beta, const float *h, const float *ysq, const float *host_gram,
+                                   const int32_t *indptr, const int32_t *indices, int64_t n_rows,
+                                   int32_t n_types, double *out, void *stream)
+{
+    FDB_REQUIRE(n_rows >= 0, "negative n_rows");
+    FDB_REQUIRE(n_types >= 1 && n_types <= FDB_MAX_TYPES, "n_types must be in [1, %d], got %d", FDB_MAX_TYPES, n_types);
+    if (n_rows == 0) return FDB_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int kp = fdb_padded_types(n_types);
+    // stage the padded Gram through a small async allocation (stream ordered)
+    float *gram_dev = nullptr, *gram_pad = nullptr;
+    FDB_CUDA(cudaMallocAsync((void **)&gram_dev, (size_t)n_types * n_types * 4 + (size_t)kp * kp * 4, st));
+    gram_pad = gram_dev + (size_t)n_types * n_types;
+    FDB_CUDA(cudaMemcpyAsync(gram_dev, host_gram, (size_t)n_types * n_types * 4, cudaMemcpyHostToDevice, st));
+    pad_gram_kernel<<<1, 256, 0, st>>>(gram_dev, n_types, kp, gram_pad);
+    const int grid = (int)std::min<int64_t>(ceil_div(n_rows, 8), (int64_t)kNumSM * 8);
+    const size_t smem = (size_t)kp * kp * 4;
+    if (kp <= 32)
+        objective_kernel<1><<<grid, 256, smem, st>>>(beta, h, ysq, gram_pad, indptr, indices, n_rows, kp, out);
+    else
+        objective_kernel<2><<<grid, 256, smem, st>>>(beta, h, ysq, gram_pad, indptr, indices, n_rows, kp, out);
+    FDB_LAUNCH_CHECK("objective_kernel");
+    FDB_CUDA(cudaFreeAsync(gram_dev, st));
+    return FDB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fdb_finish(const float *beta, const int32_t *order, int64_t n_rows, int32_t n_types,
+                          double *beta_out, double *prop_out, void *stream)
+{
+    FDB_REQUIRE(n_rows >= 0, "negative n_rows");
+    FDB_REQUIRE(n_types >= 1 && n_types <= FDB_MAX_TYPES, "n_types must be in [1, %d], got %d", FDB_MAX_TYPES, n_types);
+    if (n_rows == 0) return FDB_OK;
+    const int grid = (int)std::min<int64_t>(ceil_div(n_rows, 8), (int64_t)kNumSM * 16);
+    finish_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(beta, order, n_rows, fdb_padded_types(n_types), n_types,
+                                                         beta_out, prop_out);
+    FDB_LAUNCH_CHECK("finish_kernel");
+    return FDB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fdb_rows_gather(const float *src, const int32_t *rows, int64_t n_list, int32_t row_floats,
+                               float *dst, void *stream)
+{
+    FDB_REQUIRE(n_list >= 0 && row_floats > 0 && row_floats % 4 == 0, "row_floats must be a positive multiple of 4");
+    if (n_list == 0) return FDB_OK;
+    const int chunks = row_floats / 4;
+    rows_gather_kernel<<<(int)ceil_div(n_list * chunks, 256), 256, 0, (cudaStream_t)stream>>>(src, rows, n_list,
+                                                                                             chunks, dst);
+    FDB_LAUNCH_CHECK("rows_gather_kernel");
+    return FDB_OK;
+}

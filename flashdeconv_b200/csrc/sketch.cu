@@ -1,0 +1,391 @@
+// Kernel family 1/2: log-CPM + leverage-weighted CountSketch of the spot-by-gene CSR,
+// and the thin contraction against the sketched reference.
+//
+// Reference semantics (upstream file:line):
+//   core/deconv.py:321        Y_subset = Y[:, gene_idx]   -> here: gene_bucket[g] < 0 masks a gene out
+//   core/deconv.py:183-188    lib = row sum over selected genes, 0 -> 1;  y~ = log1p(1e4/lib * y)
+//   core/sketching.py:195     Y_s = Y~ @ Omega, Omega has ONE entry per gene (bucket, weight)
+//   core/solver.py:223,348    H = X_s Y_s^T,  YtY = sum Y_s^2
+//
+// Mapping: one warp per spot (CSR row).  The row is streamed once with coalesced loads that
+// bypass L1 (read-once data) while the per-gene tables stay L1-resident; a register cache
+// keeps (bucket, count, weight) of the first 32*kCache entries so the second pass (which
+// needs the library size) does not touch memory again.  The 512-bucket accumulator is a
+// per-warp shared-memory array updated with shared atomics (fp32 RED).
+//
+// HBM-bound: algorithmic bytes = 8*nnz + 4*(N+1) read, + 4*d*N written (materialising form)
+// or 4*(Kp+1)*N written (fused form).
+#include "fdb_common.cuh"
+
+namespace fdb {
+
+constexpr int kCache = 16;   // register-cached chunks of 32 entries per row
+
+struct RowCache {
+    int b[kCache];
+    float v[kCache];
+    float w[kCache];
+};
+
+// Pass 1 of a row: library size over selected genes + fill the register cache.
+// Entries past 32*kCache are summed here and re-read by the caller's tail loop.
+__device__ __forceinline__ float row_pass1(const int32_t *__restrict__ indices,
+                                           const float *__restrict__ counts,
+                                           const int32_t *__restrict__ gene_bucket,
+                                           const float *__restrict__ gene_weight, int64_t s,
+                                           int64_t e, int lane, RowCache &rc)
+{
+    float lib = 0.f;
+#pragma unroll
+    for (int c = 0; c < kCache; ++c) {
+        const int64_t j = s + lane + 32 * c;
+        int b = -1;
+        float v = 0.f, w = 0.f;
+        if (j < e) {
+            const int g = ld_stream(indices + j);
+            v = ld_stream(counts + j);
+            b = __ldg(gene_bucket + g);
+            if (b >= 0) {
+                w = __ldg(gene_weight + g);
+                lib += v;
+            }
+        }
+        rc.b[c] = b;
+        rc.v[c] = v;
+        rc.w[c] = w;
+    }
+    for (int64_t j = s + lane + 32 * kCache; j < e; j += 32) {
+        const int g = ld_stream(indices + j);
+        if (__ldg(gene_bucket + g) >= 0) lib += ld_stream(counts + j);
+    }
+    lib = warp_sum(lib);
+    return lib == 0.f ? 1.f : lib;
+}
+
+// ------------------------------------------------------------------------------------
+// materialising form: writes Y_s (N x d)
+// ------------------------------------------------------------------------------------
+template <typename IndPtr, bool LOGCPM>
+__global__ void __launch_bounds__(512)
+sketch_rows_kernel(const IndPtr *__restrict__ indptr, const int32_t *__restrict__ indices,
+                   const float *__restrict__ counts, int64_t n_spots,
+                   const int32_t *__restrict__ gene_bucket, const float *__restrict__ gene_weight,
+                   int d, float *__restrict__ y_sketch)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warps_per_cta = blockDim.x >> 5;
+    float *acc = smem + (size_t)warp * d;
+    for (int c = lane; c < d; c += 32) acc[c] = 0.f;
+    __syncwarp();
+
+    RowCache rc;
+    for (int64_t row = (int64_t)blockIdx.x * warps_per_cta + warp; row < n_spots;
+         row += (int64_t)gridDim.x * warps_per_cta) {
+        const int64_t s = load_ptr(indptr, row), e = load_ptr(indptr, row + 1);
+        const float scale = 1e4f / row_pass1(indices, counts, gene_bucket, gene_weight, s, e, lane, rc);
+        auto xform = [&](float v) { return LOGCPM ? log1pf(v * scale) : v; };
+#pragma unroll
+        for (int c = 0; c < kCache; ++c)
+            if (rc.b[c] >= 0) atomicAdd(acc + rc.b[c], xform(rc.v[c]) * rc.w[c]);
+        for (int64_t j = s + lane + 32 * kCache; j < e; j += 32) {
+            const int g = ld_stream(indices + j);
+            const int b = __ldg(gene_bucket + g);
+            if (b >= 0) atomicAdd(acc + b, xform(ld_stream(counts + j)) * __ldg(gene_weight + g));
+        }
+        __syncwarp();
+        float *out = y_sketch + row * (int64_t)d;
+        for (int c = lane * 4; c < d; c += 128) {            // d % 4 == 0 checked on the host
+            const float4 val = *reinterpret_cast<float4 *>(acc + c);
+            *reinterpret_cast<float4 *>(acc + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+            __stcs(reinterpret_cast<float4 *>(out + c), val);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// fused form: H[i,:] = sum_e c_e * X_s^T[bucket_e, :]  (no Y_s), ysq_i = sum_b acc_b^2
+// NK = ceil(Kp / 32): lane owns types lane (+32).
+// ------------------------------------------------------------------------------------
+template <typename IndPtr, int NK>
+__global__ void __launch_bounds__(512)
+sketch_contract_kernel(const IndPtr *__restrict__ indptr, const int32_t *__restrict__ indices,
+                       const float *__restrict__ counts, int64_t n_spots,
+                       const int32_t *__restrict__ gene_bucket,
+                       const float *__restrict__ gene_weight, int d,
+                       const float *__restrict__ x_sketch_t, int kp,
+                       const int32_t *__restrict__ row_map, float *__restrict__ h,
+                       float *__restrict__ ysq)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warps_per_cta = blockDim.x >> 5;
+    const int xrow = NK * 32;                       // smem row stride of X_s^T (padded, zero filled)
+    float *xs = smem;                               // d x xrow
+    float *acc = smem + (size_t)d * xrow + (size_t)warp * d;
+    for (int i = threadIdx.x; i < d * xrow; i += blockDim.x) {
+        const int r = i / xrow, c = i - r * xrow;
+        xs[i] = c < kp ? __ldg(x_sketch_t + (size_t)r * kp + c) : 0.f;
+    }
+    for (int c = lane; c < d; c += 32) acc[c] = 0.f;
+    __syncthreads();
+
+    RowCache rc;
+    for (int64_t row = (int64_t)blockIdx.x * warps_per_cta + warp; row < n_spots;
+         row += (int64_t)gridDim.x * warps_per_cta) {
+        const int64_t s = load_ptr(indptr, row), e = load_ptr(indptr, row + 1);
+        const float scale = 1e4f / row_pass1(indices, counts, gene_bucket, gene_weight, s, e, lane, rc);
+        float h0 = 0.f, h1 = 0.f;
+        auto consume = [&](int b, float c) {
+            // every lane calls this with its own (b, c); selected entries are broadcast one by one
+            if (b >= 0) atomicAdd(acc + b, c);
+            unsigned m = __ballot_sync(kFull, b >= 0);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const float cb = __shfl_sync(kFull, c, src);
+                const int bb = __shfl_sync(kFull, b, src);
+                h0 = fmaf(cb, xs[bb * xrow + lane], h0);
+                if (NK == 2) h1 = fmaf(cb, xs[bb * xrow + 32 + lane], h1);
+            }
+        };
+#pragma unroll
+        for (int c = 0; c < kCache; ++c) {
+            if (s + 32 * c >= e) break;             // warp-uniform
+            consume(rc.b[c], rc.b[c] >= 0 ? log1pf(rc.v[c] * scale) * rc.w[c] : 0.f);
+        }
+        for (int64_t j0 = s + 32 * kCache; j0 < e; j0 += 32) {
+            const int64_t j = j0 + lane;
+            int b = -1;
+            float c = 0.f;
+            if (j < e) {
+                const int g = ld_stream(indices + j);
+                b = __ldg(gene_bucket + g);
+                if (b >= 0) c = log1pf(ld_stream(counts + j) * scale) * __ldg(gene_weight + g);
+            }
+            consume(b, c);
+        }
+        __syncwarp();
+        float sq = 0.f;
+        for (int c = lane * 4; c < d; c += 128) {
+            const float4 a = *reinterpret_cast<float4 *>(acc + c);
+            *reinterpret_cast<float4 *>(acc + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+            sq = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, sq))));
+        }
+        sq = warp_sum(sq);
+        const int64_t orow = row_map ? (int64_t)__ldg(row_map + row) : row;
+        float *out = h + orow * kp;
+        if (lane < kp) out[lane] = h0;
+        if (NK == 2 && 32 + lane < kp) out[32 + lane] = h1;
+        if (lane == 0) ysq[orow] = sq;
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// unfused contraction (API / parity form): H = Y_s X_s^T, ysq = rowwise ||y_s||^2
+// one warp per spot, X_s staged in shared memory
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+contract_kernel(const float *__restrict__ y_sketch, const float *__restrict__ x_sketch,
+                int64_t n_spots, int d, int n_types, int kp, float *__restrict__ h,
+                float *__restrict__ ysq)
+{
+    extern __shared__ __align__(16) float xs[];     // n_types x d
+    for (int i = threadIdx.x; i < n_types * d; i += blockDim.x) xs[i] = __ldg(x_sketch + i);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warps_per_cta = blockDim.x >> 5;
+    for (int64_t row = (int64_t)blockIdx.x * warps_per_cta + warp; row < n_spots;
+         row += (int64_t)gridDim.x * warps_per_cta) {
+        const float *y = y_sketch + row * (int64_t)d;
+        float sq = 0.f;
+        for (int c = lane; c < d; c += 32) {
+            const float v = __ldcs(y + c);
+            sq = fmaf(v, v, sq);
+        }
+        sq = warp_sum(sq);
+        if (lane == 0) ysq[row] = sq;
+        for (int k = 0; k < kp; ++k) {
+            float a = 0.f;
+            if (k < n_types)
+                for (int c = lane; c < d; c += 32) a = fmaf(y[c], xs[k * d + c], a);
+            a = warp_sum(a);
+            if (lane == 0) h[row * kp + k] = a;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// (f1) per-gene moments of log1p(CP10k) over ALL genes: utils/genes.py:52-83
+// warp per row; fp64 atomics into the G-long accumulators (L2-resident, 2*8*G bytes)
+// ------------------------------------------------------------------------------------
+template <typename IndPtr>
+__global__ void __launch_bounds__(256)
+gene_moments_kernel(const IndPtr *__restrict__ indptr, const int32_t *__restrict__ indices,
+                    const float *__restrict__ counts, int64_t n_spots, double *__restrict__ sums,
+                    double *__restrict__ sumsq)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = warp_global; row < n_spots; row += n_warps) {
+        const int64_t s = load_ptr(indptr, row), e = load_ptr(indptr, row + 1);
+        float lib = 0.f;
+        for (int64_t j = s + lane; j < e; j += 32) lib += __ldg(counts + j);
+        lib = warp_sum(lib);
+        const float scale = 1e4f / fmaxf(lib, 1.f);
+        for (int64_t j = s + lane; j < e; j += 32) {
+            const double z = (double)log1pf(__ldg(counts + j) * scale);
+            const int g = ld_stream(indices + j);
+            atomicAdd(sums + g, z);
+            atomicAdd(sumsq + g, z * z);
+        }
+    }
+}
+
+static int pick_grid(int64_t n_rows, int warps_per_cta, int ctas_per_sm)
+{
+    int64_t want = ceil_div(n_rows, warps_per_cta);
+    int64_t cap = (int64_t)kNumSM * ctas_per_sm;
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+}  // namespace fdb
+
+using namespace fdb;
+
+template <typename IndPtr, bool LOGCPM>
+static int launch_rows(const void *indptr, const int32_t *indices, const float *counts, int64_t n_spots,
+                       const int32_t *gene_bucket, const float *gene_weight, int d, float *y_sketch,
+                       cudaStream_t st)
+{
+    int warps = 16;
+    while (warps > 1 && (size_t)warps * d * 4 > 96 * 1024) warps >>= 1;
+    const size_t smem = (size_t)warps * d * 4;
+    auto kern = sketch_rows_kernel<IndPtr, LOGCPM>;
+    FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<pick_grid(n_spots, warps, 2), warps * 32, smem, st>>>((const IndPtr *)indptr, indices, counts, n_spots,
+                                                                 gene_bucket, gene_weight, d, y_sketch);
+    FDB_LAUNCH_CHECK("sketch_rows_kernel");
+    return FDB_OK;
+}
+
+static int sketch_rows(const void *indptr, int is64, const int32_t *indices, const float *counts, int64_t n_spots,
+                       int32_t n_genes, const int32_t *gene_bucket, const float *gene_weight, int32_t d,
+                       float *y_sketch, void *stream, bool logcpm)
+{
+    FDB_REQUIRE(n_spots >= 0 && n_genes >= 0, "negative shape");
+    FDB_REQUIRE(d > 0 && d % 4 == 0 && d <= 8192, "sketch_dim must be a positive multiple of 4 (<= 8192), got %d", d);
+    if (n_spots == 0) return FDB_OK;
+    FDB_REQUIRE(indptr && gene_bucket && gene_weight && y_sketch, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (is64)
+        return logcpm ? launch_rows<int64_t, true>(indptr, indices, counts, n_spots, gene_bucket, gene_weight, d, y_sketch, st)
+                      : launch_rows<int64_t, false>(indptr, indices, counts, n_spots, gene_bucket, gene_weight, d, y_sketch, st);
+    return logcpm ? launch_rows<int32_t, true>(indptr, indices, counts, n_spots, gene_bucket, gene_weight, d, y_sketch, st)
+                  : launch_rows<int32_t, false>(indptr, indices, counts, n_spots, gene_bucket, gene_weight, d, y_sketch, st);
+}
+
+extern "C" __attribute__((visibility("default"))) int fdb_sketch_logcpm_csr(
+    const void *indptr, int indptr_is_int64, const int32_t *indices, const float *counts, int64_t n_spots,
+    int32_t n_genes, const int32_t *gene_bucket, const float *gene_weight, int32_t d, float *y_sketch, void *stream)
+{
+    return sketch_rows(indptr, indptr_is_int64, indices, counts, n_spots, n_genes, gene_bucket, gene_weight, d,
+                       y_sketch, stream, true);
+}
+
+extern "C" __attribute__((visibility("default"))) int fdb_sketch_project_csr(
+    const void *indptr, int indptr_is_int64, const int32_t *indices, const float *values, int64_t n_spots,
+    int32_t n_genes, const int32_t *gene_bucket, const float *gene_weight, int32_t d, float *y_sketch, void *stream)
+{
+    return sketch_rows(indptr, indptr_is_int64, indices, values, n_spots, n_genes, gene_bucket, gene_weight, d,
+                       y_sketch, stream, false);
+}
+
+extern "C" __attribute__((visibility("default"))) int fdb_contract(const float *y_sketch, const float *x_sketch, int64_t n_spots, int32_t d,
+                            int32_t n_types, float *h, float *ysq, void *stream)
+{
+    FDB_REQUIRE(n_spots >= 0 && d > 0 && n_types > 0, "bad shape");
+    if (n_spots == 0) return FDB_OK;
+    const size_t smem = (size_t)n_types * d * 4;
+    FDB_REQUIRE(smem <= 200 * 1024, "X_s (%d x %d) does not fit in shared memory", n_types, d);
+    FDB_CUDA(cudaFuncSetAttribute(contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int kp = fdb_padded_types(n_types);
+    const int grid = pick_grid(n_spots, 8, smem > 100 * 1024 ? 1 : 2);
+    contract_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(y_sketch, x_sketch, n_spots, d, n_types,
+                                                              kp, h, ysq);
+    FDB_LAUNCH_CHECK("contract_kernel");
+    return FDB_OK;
+}
+
+template <typename IndPtr, int NK>
+static int launch_fused(const void *indptr, const int32_t *indices, const float *counts,
+                        int64_t n_spots, const int32_t *gene_bucket, const float *gene_weight, int d,
+                        const float *x_sketch_t, int kp, const int32_t *row_map, float *h, float *ysq,
+                        cudaStream_t st)
+{
+    const size_t xs_bytes = (size_t)d * NK * 32 * 4;
+    int warps = 16;
+    while (warps > 1 && xs_bytes + (size_t)warps * d * 4 > 110 * 1024) warps >>= 1;
+    size_t smem = xs_bytes + (size_t)warps * d * 4;
+    int per_sm = 2;
+    if (smem > 110 * 1024) {                       // large X_s^T: one CTA per SM, as many warps as fit
+        per_sm = 1;
+        warps = 16;
+        while (warps > 1 && xs_bytes + (size_t)warps * d * 4 > 220 * 1024) warps >>= 1;
+        smem = xs_bytes + (size_t)warps * d * 4;
+    }
+    if (smem > 227 * 1024) {
+        set_error("sketch_dim %d x %d types does not fit in shared memory", d, kp);
+        return FDB_ERR_UNSUPPORTED;
+    }
+    auto kern = sketch_contract_kernel<IndPtr, NK>;
+    FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = pick_grid(n_spots, warps, per_sm);
+    kern<<<grid, warps * 32, smem, st>>>((const IndPtr *)indptr, indices, counts, n_spots, gene_bucket,
+                                         gene_weight, d, x_sketch_t, kp, row_map, h, ysq);
+    FDB_LAUNCH_CHECK("sketch_contract_kernel");
+    return FDB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fdb_sketch_contract_csr(const void *indptr, int indptr_is_int64, const int32_t *indices,
+                                       const float *counts, int64_t n_spots, int32_t n_genes,
+                                       const int32_t *gene_bucket, const float *gene_weight, int32_t d,
+                                       const float *x_sketch_t, int32_t n_types, const int32_t *row_map,
+                                       float *h, float *ysq, void *stream)
+{
+    FDB_REQUIRE(n_spots >= 0 && n_genes >= 0, "negative shape");
+    FDB_REQUIRE(d > 0 && d % 4 == 0, "sketch_dim must be a positive multiple of 4, got %d", d);
+    FDB_REQUIRE(n_types > 0 && n_types <= FDB_MAX_TYPES, "n_types must be in [1, %d], got %d", FDB_MAX_TYPES, n_types);
+    if (n_spots == 0) return FDB_OK;
+    FDB_REQUIRE(indptr && gene_bucket && gene_weight && x_sketch_t && h && ysq, "null pointer");
+    const int kp = fdb_padded_types(n_types);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (kp <= 32)
+        return indptr_is_int64
+                   ? launch_fused<int64_t, 1>(indptr, indices, counts, n_spots, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, h, ysq, st)
+                   : launch_fused<int32_t, 1>(indptr, indices, counts, n_spots, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, h, ysq, st);
+    return indptr_is_int64
+               ? launch_fused<int64_t, 2>(indptr, indices, counts, n_spots, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, h, ysq, st)
+               : launch_fused<int32_t, 2>(indptr, indices, counts, n_spots, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, h, ysq, st);
+}
+
+extern "C" __attribute__((visibility("default"))) int fdb_gene_moments_csr(const void *indptr, int indptr_is_int64, const int32_t *indices,
+                                    const float *counts, int64_t n_spots, int32_t n_genes, double *sums,
+                                    double *sumsq, void *stream)
+{
+    FDB_REQUIRE(n_spots >= 0 && n_genes >= 0, "negative shape");
+    if (n_spots == 0) return FDB_OK;
+    const int grid = pick_grid(n_spots, 8, 8);
+    if (indptr_is_int64)
+        gene_moments_kernel<int64_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const int64_t *)indptr, indices, counts, n_spots, sums, sumsq);
+    else
+        gene_moments_kernel<int32_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const int32_t *)indptr, indices, counts, n_spots, sums, sumsq);
+    FDB_LAUNCH_CHECK("gene_moments_kernel");
+    return FDB_OK;
+}

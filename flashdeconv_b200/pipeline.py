@@ -1,0 +1,339 @@
+"""Device-resident hot path: sketch -> graph -> BCD, driven through the C ABI.
+
+This is the host-side orchestration that `FlashDeconv.fit` (estimator.py) and
+`bench.py` share.  torch is used only for device memory, streams and (in
+tiling.py) torch.distributed; every arithmetic step on spots is a libfdb200 call.
+
+Reference steps covered (core/deconv.py:321-398): gene subsetting + log-CPM +
+sketch (fused, kernel 1/2), spatial graph (kernel 3), auto lambda, BCD solve
+(kernel 4), objective, proportion normalisation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+from scipy import sparse
+
+from . import _native
+from ._native import check, lib
+
+GRAPH_MODES = {"knn": 0, "radius": 1, "grid": 2}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream(torch):
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@dataclass
+class DeviceCSR:
+    """Spot-by-gene counts on the device: indptr int64|int32, indices int32, data float32."""
+    indptr: "object"
+    indices: "object"
+    data: "object"
+    shape: tuple
+
+    @property
+    def nnz(self) -> int:
+        return int(self.indices.numel())
+
+
+def csr_to_device(Y, device="cuda", non_blocking=True) -> DeviceCSR:
+    """Accepts a scipy sparse matrix, a dense ndarray (converted to CSR on the host) or a DeviceCSR."""
+    torch = _native.require_cuda()
+    if isinstance(Y, DeviceCSR):
+        return Y
+    if not sparse.issparse(Y):
+        Y = sparse.csr_matrix(np.asarray(Y))
+    Y = Y.tocsr()
+    if not Y.has_canonical_format:
+        Y = Y.copy()
+        Y.sum_duplicates()
+    ip = np.ascontiguousarray(Y.indptr)
+    if ip.dtype not in (np.int32, np.int64):
+        ip = ip.astype(np.int64)
+    ix = np.ascontiguousarray(Y.indices, dtype=np.int32)
+    dv = np.ascontiguousarray(Y.data, dtype=np.float32)
+    dev = torch.device(device)
+    to = lambda a: torch.from_numpy(a).to(dev, non_blocking=non_blocking)
+    return DeviceCSR(to(ip), to(ix), to(dv), tuple(Y.shape))
+
+
+@dataclass
+class SketchTables:
+    """Host-built CountSketch tables (core/sketching.py:48-84) expanded to the FULL gene axis."""
+    gene_bucket: np.ndarray      # int32[G], -1 for unselected genes
+    gene_weight: np.ndarray      # float32[G]
+    bucket: np.ndarray           # int64[G_sel]  (bit-exact with the reference's Omega.indices)
+    sign: np.ndarray             # int64[G_sel]
+    weight: np.ndarray           # float64[G_sel]
+    X_sketch: np.ndarray         # float64 K x d
+    gram: np.ndarray             # float64 K x K
+    d: int
+
+
+def countsketch_table(n_genes: int, d: int, leverage, seed):
+    """Bucket / sign / weight per selected gene.  numpy's legacy RandomState is called in the
+    reference's order (randint, then choice: core/sketching.py:58-59) so draws are bit-identical."""
+    if seed is None or seed is np.random:
+        rng = np.random.mtrand._rand
+    elif isinstance(seed, (int, np.integer)):
+        rng = np.random.RandomState(seed)
+    elif isinstance(seed, np.random.RandomState):
+        rng = seed
+    else:
+        raise ValueError(f"'{seed}' cannot be used to seed a numpy.random.RandomState instance. "
+                         f"Expected None, int, or np.random.RandomState, got {type(seed)}.")
+    if leverage is None:
+        p = np.full(n_genes, 1.0 / max(n_genes, 1))
+    else:
+        p = np.asarray(leverage, dtype=np.float64)
+        p = p / (p.sum() + 1e-10)
+    bucket = rng.randint(0, d, size=n_genes)
+    sign = rng.choice([-1, 1], size=n_genes)
+    entry = sign * np.clip(np.sqrt(p * n_genes + 1e-10), 0.1, 10.0)
+    norms = np.maximum(np.sqrt(np.bincount(bucket, weights=entry * entry, minlength=d)), 1e-10)
+    weight = entry * (np.sqrt(n_genes / d) / norms[bucket])
+    return bucket.astype(np.int64), sign.astype(np.int64), weight
+
+
+def build_tables(X, gene_idx, leverage, d, seed, n_genes_total) -> SketchTables:
+    """Everything about the reference side that stays on the host (K x G_sel work)."""
+    X = np.asarray(X, dtype=np.float64)
+    gene_idx = np.asarray(gene_idx, dtype=np.intp)
+    bucket, sign, weight = countsketch_table(len(gene_idx), d, leverage, seed)
+    Xsel = X[:, gene_idx]
+    Xt = np.log1p(Xsel / (Xsel.sum(axis=1, keepdims=True) + 1e-10) * 1e4)      # core/deconv.py:194-195
+    Xs = np.zeros((X.shape[0], d))
+    np.add.at(Xs.T, bucket, (Xt * weight).T)                                   # X~ @ Omega, core/sketching.py:202
+    gb = np.full(n_genes_total, -1, dtype=np.int32)
+    gw = np.zeros(n_genes_total, dtype=np.float32)
+    gb[gene_idx] = bucket
+    gw[gene_idx] = weight
+    return SketchTables(gb, gw, bucket, sign, weight, Xs, Xs @ Xs.T, d)
+
+
+@dataclass
+class DeviceGraph:
+    order: "object"          # int32[N]  tile position -> input index
+    rank: "object"           # int32[N]  input index -> tile position
+    indptr: "object"         # int32[N+1] (tile order)
+    indices: "object"        # int32[nnz] (tile-order positions, ascending)
+    nnz: int
+    radius: Optional[float] = None
+
+    def to_scipy(self):
+        """Adjacency in INPUT order with ascending columns, float64 ones (FlashDeconv.adjacency_)."""
+        torch = _native.require_cuda()
+        n = int(self.order.numel())
+        out_ptr = torch.empty(n + 1, dtype=torch.int32, device=self.order.device)
+        out_idx = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=self.order.device)
+        ws = torch.empty(8 * (n + 1) + (1 << 16), dtype=torch.uint8, device=self.order.device)
+        check(lib.fdb_graph_to_input_order(_ptr(self.indptr), _ptr(self.indices), _ptr(self.order), _ptr(self.rank),
+                                           n, _ptr(out_ptr), _ptr(out_idx), _ptr(ws), ws.numel(), _stream(torch)),
+              "graph_to_input_order")
+        ip = out_ptr.cpu().numpy()
+        ix = out_idx[: self.nnz].cpu().numpy()
+        return sparse.csr_matrix((np.ones(self.nnz, dtype=np.float64), ix, ip), shape=(n, n))
+
+
+def build_graph(coords_dev, method="knn", k=6, radius=None) -> DeviceGraph:
+    """coords_dev: float64 CUDA tensor N x 2 (input order)."""
+    torch = _native.require_cuda()
+    if method not in GRAPH_MODES:
+        raise ValueError(f"Unknown method: {method}")
+    if method == "radius" and radius is None:
+        raise ValueError("radius must be specified for radius method")
+    if coords_dev.dim() != 2 or coords_dev.shape[1] == 0:
+        raise ValueError("coords must be 2D with at least 1 coordinate dimension, "
+                         f"got shape {tuple(coords_dev.shape)}")
+    if coords_dev.shape[1] != 2:
+        raise NotImplementedError("libfdb200 builds 2-D spatial graphs; got coords with "
+                                  f"{coords_dev.shape[1]} columns")
+    n = int(coords_dev.shape[0])
+    dev = coords_dev.device
+    coords_dev = coords_dev.contiguous().to(torch.float64)
+    order = torch.empty(n, dtype=torch.int32, device=dev)
+    rank = torch.empty(n, dtype=torch.int32, device=dev)
+    indptr = torch.zeros(n + 1, dtype=torch.int32, device=dev)
+    k_eff = int(k) if method == "knn" else 1
+    ws_bytes = int(lib.fdb_graph_workspace_bytes(n, max(k_eff, 1)))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    cap = max(2 * max(k_eff, 1) * n, 16) if method == "knn" else max(12 * n, 16)
+    nnz, rad = C.c_int64(0), C.c_double(0.0)
+    for _ in range(3):
+        indices = torch.empty(cap, dtype=torch.int32, device=dev)
+        rc = lib.fdb_graph_build(_ptr(coords_dev), n, GRAPH_MODES[method], k_eff, float(radius or 0.0),
+                                 _ptr(order), _ptr(rank), _ptr(indptr), _ptr(indices), cap,
+                                 C.byref(nnz), C.byref(rad), _ptr(ws), ws_bytes, _stream(torch))
+        if rc == -3 and nnz.value > cap:          # radius graphs: degree unknown up front
+            cap = int(nnz.value)
+            continue
+        check(rc, "graph_build")
+        break
+    return DeviceGraph(order, rank, indptr, indices, int(nnz.value), rad.value if method != "knn" else None)
+
+
+@dataclass
+class SolveResult:
+    beta: np.ndarray                   # N x K float64, input order
+    proportions: np.ndarray            # N x K float64
+    info: dict
+    lambda_used: float
+    graph: DeviceGraph
+    tables: SketchTables
+    timings: dict = field(default_factory=dict)
+
+
+class DevicePath:
+    """One deconvolution on one GPU.  All big buffers are torch CUDA tensors owned by this object."""
+
+    def __init__(self, csr: DeviceCSR, coords_dev, tables: SketchTables, n_types: int):
+        self.torch = _native.require_cuda()
+        self.csr, self.coords, self.tables, self.K = csr, coords_dev, tables, int(n_types)
+        self.Kp = _native.padded_types(self.K)
+        self.dev = csr.indices.device
+        t = self.torch
+        self.gene_bucket = t.from_numpy(tables.gene_bucket).to(self.dev)
+        self.gene_weight = t.from_numpy(tables.gene_weight).to(self.dev)
+        xst = np.zeros((tables.d, self.Kp), dtype=np.float32)
+        xst[:, : self.K] = tables.X_sketch.T
+        self.x_sketch_t = t.from_numpy(xst).to(self.dev)
+        self.gram32 = np.ascontiguousarray(tables.gram, dtype=np.float32)
+        n = csr.shape[0]
+        self.h = t.empty((n, self.Kp), dtype=t.float32, device=self.dev)
+        self.ysq = t.empty(n, dtype=t.float32, device=self.dev)
+        self.beta_a = t.empty((n, self.Kp), dtype=t.float32, device=self.dev)
+        self.beta_b = t.empty((n, self.Kp), dtype=t.float32, device=self.dev)
+        self.state = t.zeros(16, dtype=t.int32, device=self.dev)
+        self.graph: Optional[DeviceGraph] = None
+
+    # ---- stages -----------------------------------------------------------------------
+    def stage_graph(self, method="knn", k=6, radius=None):
+        self.graph = build_graph(self.coords, method, k, radius)
+        return self.graph
+
+    def stage_sketch(self):
+        """Fused log-CPM + CountSketch + contraction; rows land in tile order (needs the graph)."""
+        c, tb = self.csr, self.tables
+        row_map = self.graph.rank if self.graph is not None else None
+        check(lib.fdb_sketch_contract_csr(_ptr(c.indptr), int(c.indptr.dtype == self.torch.int64), _ptr(c.indices),
+                                          _ptr(c.data), c.shape[0], c.shape[1], _ptr(self.gene_bucket),
+                                          _ptr(self.gene_weight), tb.d, _ptr(self.x_sketch_t), self.K,
+                                          _ptr(row_map), _ptr(self.h), _ptr(self.ysq), _stream(self.torch)),
+              "sketch_contract_csr")
+
+    def lambda_auto(self, alpha=0.005) -> float:
+        """core/spatial.py:181-190 with mean degree = nnz / N."""
+        n = self.csr.shape[0]
+        mean_deg = self.graph.nnz / n if n else 0.0
+        return float(alpha * float(np.mean(np.diag(self.tables.gram))) / max(mean_deg, 1.0))
+
+    def rho_scaled(self, rho: float) -> float:
+        return float(rho) * float(np.mean(np.diag(self.tables.gram)))          # core/solver.py:359-360
+
+    def stage_solve(self, lam: float, rho_scaled: float, max_iter: int, tol: float):
+        g = self.graph
+        check(lib.fdb_bcd_solve(_ptr(self.h), self.gram32.ctypes.data_as(C.c_void_p), _ptr(self.beta_a),
+                                _ptr(self.beta_b), _ptr(g.indptr), _ptr(g.indices), self.csr.shape[0], self.K,
+                                float(lam), float(rho_scaled), int(max_iter), float(tol), _ptr(self.state),
+                                _stream(self.torch)), "bcd_solve")
+
+    def read_state(self):
+        st = self.state.cpu()
+        n_iter, conv = int(st[3]), bool(int(st[4]))
+        rel = float(st[5:6].view(self.torch.float32)[0])
+        return n_iter, conv, rel
+
+    def current_beta(self, n_iter: int):
+        return self.beta_a if n_iter % 2 == 0 else self.beta_b
+
+    def objective(self, beta_dev, lam: float, rho_scaled: float) -> float:
+        t = self.torch
+        g = self.graph
+        out = t.zeros(5, dtype=t.float64, device=self.dev)
+        check(lib.fdb_objective_terms(_ptr(beta_dev), _ptr(self.h), _ptr(self.ysq),
+                                      self.gram32.ctypes.data_as(C.c_void_p), _ptr(g.indptr), _ptr(g.indices),
+                                      self.csr.shape[0], self.K, _ptr(out), _stream(t)), "objective_terms")
+        cross, quad, lap, l1, yty = out.cpu().tolist()
+        return 0.5 * (yty - 2.0 * cross + quad) + 0.5 * lam * lap + rho_scaled * l1   # core/solver.py:269-284
+
+    def finish(self, beta_dev, pinned=False):
+        t = self.torch
+        n = self.csr.shape[0]
+        b64 = t.empty((n, self.K), dtype=t.float64, device=self.dev)
+        p64 = t.empty((n, self.K), dtype=t.float64, device=self.dev)
+        check(lib.fdb_finish(_ptr(beta_dev), _ptr(self.graph.order), n, self.K, _ptr(b64), _ptr(p64), _stream(t)),
+              "finish")
+        if pinned:
+            hb = t.empty((n, self.K), dtype=t.float64, pin_memory=True)
+            hp = t.empty((n, self.K), dtype=t.float64, pin_memory=True)
+            hb.copy_(b64, non_blocking=True)
+            hp.copy_(p64, non_blocking=True)
+            t.cuda.current_stream().synchronize()
+            return hb.numpy(), hp.numpy()
+        return b64.cpu().numpy(), p64.cpu().numpy()
+
+    # ---- whole path -------------------------------------------------------------------
+    def run(self, *, method="knn", k=6, radius=None, lam="auto", rho=0.01, max_iter=100, tol=1e-4,
+            verbose=False, pinned_out=False) -> SolveResult:
+        t = self.torch
+        n = self.csr.shape[0]
+        self.stage_graph(method, k, radius)
+        self.stage_sketch()
+        lam_used = self.lambda_auto() if isinstance(lam, str) else float(lam)
+        rho_s = self.rho_scaled(rho)
+        objectives = []
+        if verbose:
+            n_iter, conv, rel = self._solve_verbose(lam_used, rho_s, max_iter, tol, objectives)
+        else:
+            self.stage_solve(lam_used, rho_s, max_iter, tol)
+            n_iter, conv, rel = self.read_state()
+        if max_iter == 0:
+            rel = 0.0
+        beta_dev = self.current_beta(n_iter)
+        obj = self.objective(beta_dev, lam_used, rho_s) if n else 0.0
+        beta, prop = self.finish(beta_dev, pinned=pinned_out)
+        info = dict(converged=conv, n_iterations=n_iter, final_objective=obj,
+                    objectives=objectives if verbose else [], final_change=rel)
+        return SolveResult(beta, prop, info, lam_used, self.graph, self.tables)
+
+    def _solve_verbose(self, lam, rho_s, max_iter, tol, objectives):
+        """Sweep-at-a-time loop used only for verbose=True (objective every 10 sweeps, core/solver.py:399-404)."""
+        g, n = self.graph, self.csr.shape[0]
+        st = _stream(self.torch)
+        check(lib.fdb_bcd_init(_ptr(self.beta_a), n, self.K, _ptr(self.state), st), "bcd_init")
+        cur, nxt = self.beta_a, self.beta_b
+        n_iter, conv, rel = 0, False, 0.0
+        for it in range(max_iter):
+            check(lib.fdb_bcd_sweep(_ptr(self.h), self.gram32.ctypes.data_as(C.c_void_p), _ptr(cur), _ptr(nxt),
+                                    _ptr(g.indptr), _ptr(g.indices), n, self.K, float(lam), float(rho_s),
+                                    float(tol), 1, _ptr(self.state), st), "bcd_sweep")
+            n_iter, conv, rel = self.read_state()
+            if it % 10 == 0 or it == max_iter - 1:
+                obj = self.objective(nxt, lam, rho_s)
+                objectives.append(obj)
+                print(f"Iteration {it}: objective = {obj:.6f}, rel_change = {rel:.6e}")
+            cur, nxt = nxt, cur
+            if conv:
+                print(f"Converged at iteration {it}")
+                break
+        return n_iter, conv, rel
+
+
+def gene_moments(csr: DeviceCSR):
+    """Per-gene sum and sum of squares of log1p(CP10k) over all spots (utils/genes.py:52-83) -> host float64."""
+    torch = _native.require_cuda()
+    G = csr.shape[1]
+    sums = torch.zeros(G, dtype=torch.float64, device=csr.indices.device)
+    sq = torch.zeros(G, dtype=torch.float64, device=csr.indices.device)
+    check(lib.fdb_gene_moments_csr(_ptr(csr.indptr), int(csr.indptr.dtype == torch.int64), _ptr(csr.indices),
+                                   _ptr(csr.data), csr.shape[0], G, _ptr(sums), _ptr(sq), _stream(torch)),
+          "gene_moments_csr")
+    return sums.cpu().numpy(), sq.cpu().numpy()

@@ -1,0 +1,180 @@
+/*
+ * fdb200.h -- C ABI of libfdb200.so: the B200 (sm_100a) implementation of FlashDeconv's
+ * data-parallel hot path.
+ *
+ * The reference (cafferychen777/flashdeconv v0.1.6) is pure Python and has NO FFI layer;
+ * each entry point below names the reference function (file:line under the upstream repo)
+ * whose arithmetic it replaces.  A maintainer binds them with ctypes exactly as
+ * flashdeconv_b200/_native.py does.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative fdb_status otherwise; the message is
+ *     available from fdb_last_error() (thread-local);
+ *   - all pointers are DEVICE pointers unless the parameter name starts with `host_`;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued asynchronously on it,
+ *     functions documented "syncs" block the host on that stream once;
+ *   - nothing is allocated behind the caller's back: scratch memory is passed in as
+ *     (workspace, workspace_bytes) sized by the matching *_workspace_bytes() query;
+ *   - no torch / C++ types cross the boundary.
+ *
+ * Device layouts
+ *   spots live in "tile order" (a spatially coherent permutation produced by
+ *   fdb_graph_build); `order[p]` = original index of the spot at position p, `rank[i]` =
+ *   position of original spot i.  Spot-by-type matrices (H, beta) are row-major
+ *   n_rows x Kp float32 with Kp = fdb_padded_types(K) (K rounded up to a multiple of 4, so
+ *   every row is 16-byte aligned); padding columns are zero.
+ */
+#ifndef FDB200_H
+#define FDB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    FDB_OK = 0,
+    FDB_ERR_ARG = -1,        /* invalid argument                       */
+    FDB_ERR_CUDA = -2,       /* a CUDA runtime call or launch failed   */
+    FDB_ERR_WORKSPACE = -3,  /* workspace too small                    */
+    FDB_ERR_UNSUPPORTED = -4 /* valid request outside what is built    */
+} fdb_status;
+
+#define FDB_MAX_TYPES 64     /* K handled by the register-resident BCD kernels */
+
+int fdb_abi_version(void);
+const char *fdb_last_error(void);
+int fdb_padded_types(int n_types);                       /* Kp */
+
+/* ---------------------------------------------------------------------------------------
+ * (a1 + a3) log-CPM fused with the leverage-weighted CountSketch, one pass over the FULL
+ * spot-by-gene CSR.  Replaces FlashDeconv._preprocess_data "log_cpm" (core/deconv.py:177-197)
+ * + Y[:, gene_idx] (core/deconv.py:321) + project_to_sketch (core/sketching.py:190-199).
+ *   gene_bucket[g] in [0,d) for selected genes, -1 otherwise;  gene_weight[g] = Omega entry.
+ *   lib_i = sum of counts over SELECTED genes (0 -> 1), y~ = log1p(1e4 * count / lib_i).
+ *   y_sketch: n_spots x d float32, row i at y_sketch + i*d (input spot order).
+ * ------------------------------------------------------------------------------------- */
+int fdb_sketch_logcpm_csr(const void *indptr, int indptr_is_int64, const int32_t *indices,
+                          const float *counts, int64_t n_spots, int32_t n_genes,
+                          const int32_t *gene_bucket, const float *gene_weight, int32_t d,
+                          float *y_sketch, void *stream);
+
+/* (a3 alone) Y_s = Y~ Omega for an ALREADY transformed CSR matrix -- the arithmetic of
+ * project_to_sketch (core/sketching.py:160-206) without the log-CPM step. */
+int fdb_sketch_project_csr(const void *indptr, int indptr_is_int64, const int32_t *indices,
+                           const float *values, int64_t n_spots, int32_t n_genes,
+                           const int32_t *gene_bucket, const float *gene_weight, int32_t d,
+                           float *y_sketch, void *stream);
+
+/* (a4) H = Y_s X_s^T and per-spot ||y_s||^2.  Replaces precompute_XtY (core/solver.py:204-223)
+ * and YtY (core/solver.py:348).  x_sketch: K x d row-major.  h: n_spots x Kp.  ysq: n_spots f32. */
+int fdb_contract(const float *y_sketch, const float *x_sketch, int64_t n_spots, int32_t d,
+                 int32_t n_types, float *h, float *ysq, void *stream);
+
+/* (a1 + a3 + a4) production form: never materialises Y_s.  Streams the CSR once and writes
+ *   h[row_map ? row_map[i] : i][:] = X_s . y_s,i      (n_spots x Kp, float32)
+ *   ysq[row_map ? row_map[i] : i]  = ||y_s,i||^2
+ * x_sketch_t is the TRANSPOSED sketched reference, d x Kp row-major (padding columns zero). */
+int fdb_sketch_contract_csr(const void *indptr, int indptr_is_int64, const int32_t *indices,
+                            const float *counts, int64_t n_spots, int32_t n_genes,
+                            const int32_t *gene_bucket, const float *gene_weight, int32_t d,
+                            const float *x_sketch_t, int32_t n_types, const int32_t *row_map,
+                            float *h, float *ysq, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (a5) spatial graph.  Replaces build_knn_graph (utils/graph.py:25-83), build_radius_graph
+ * (:86-133) and build_grid_graph (:136-172): float64 squared distances, k nearest OTHER
+ * spots (ties -> smaller original index), union-symmetrised, binary, ascending columns.
+ *
+ * fdb_graph_build (syncs twice: bounding box, nnz):
+ *   coords        n_spots x 2 float64, input order
+ *   mode          0 = kNN with `k`; 1 = radius graph with `radius` (d <= radius);
+ *                 2 = "grid": radius = 1.5 * median nearest-neighbour distance
+ *   order, rank   out, int32[n_spots]  (tile order <-> input order)
+ *   indptr        out, int32[n_spots + 1], tile order
+ *   indices       out, int32[indices_capacity], neighbours as tile-order positions, ascending
+ *   host_nnz      out (host), number of stored entries
+ *   host_radius   out (host, may be NULL), radius actually used for modes 1/2
+ * Returns FDB_ERR_WORKSPACE if indices_capacity is too small (host_nnz then holds the need).
+ * ------------------------------------------------------------------------------------- */
+int64_t fdb_graph_workspace_bytes(int64_t n_spots, int32_t k);
+int fdb_graph_build(const double *coords, int64_t n_spots, int32_t mode, int32_t k, double radius,
+                    int32_t *order, int32_t *rank, int32_t *indptr, int32_t *indices,
+                    int64_t indices_capacity, int64_t *host_nnz, double *host_radius,
+                    void *workspace, int64_t workspace_bytes, void *stream);
+
+/* Adjacency relabelled to INPUT order with ascending columns (what FlashDeconv.adjacency_
+ * exposes, core/deconv.py:364).  out_indptr int32[n+1], out_indices int32[nnz]. */
+int fdb_graph_to_input_order(const int32_t *indptr, const int32_t *indices, const int32_t *order,
+                             const int32_t *rank, int64_t n_spots, int32_t *out_indptr,
+                             int32_t *out_indices, void *workspace, int64_t workspace_bytes,
+                             void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (a8 + a9) Jacobi block-coordinate-descent.  Replaces _bcd_iteration_fused
+ * (core/solver.py:104-184), update_spot_with_Xty (:29-101) and the loop of bcd_solve
+ * (:385-413).
+ *
+ * State block (device, 64 bytes, zero it before the first sweep):
+ *   [0] uint32 max|delta| bits   [1] uint32 max|old| bits   [2] uint32 blocks arrived
+ *   [3] int32  sweeps completed  [4] int32 converged flag   [5] float  last rel_change
+ *
+ * fdb_bcd_sweep: one sweep over rows [0, n_rows) of beta_in -> beta_out (both n_total x Kp;
+ * rows >= n_rows are halo rows that are only read).  If `finalize` != 0 the last block to
+ * finish computes rel_change = max|delta| / (max|old| + 1e-10), bumps the sweep counter and
+ * raises the converged flag when rel_change < tol; sweeps launched after the flag is up
+ * return immediately (so a fixed number of launches can be enqueued with no host sync).
+ * host_gram: K x K float32 (host memory; passed to the kernel by value).
+ * ------------------------------------------------------------------------------------- */
+int fdb_bcd_sweep(const float *h, const float *host_gram, const float *beta_in, float *beta_out,
+                  const int32_t *indptr, const int32_t *indices, int64_t n_rows, int32_t n_types,
+                  float lambda, float rho_scaled, float tol, int32_t finalize, void *state,
+                  void *stream);
+
+/* Single-thread kernel doing the finalize step on an externally reduced state block (the
+ * multi-GPU path all-reduces words [0],[1] with MAX between sweep and finalize). */
+int fdb_bcd_finalize(void *state, float tol, void *stream);
+
+/* beta[:, :K] <- 1/K (core/solver.py:372), padding columns <- 0, state block <- 0 (state may be NULL). */
+int fdb_bcd_init(float *beta, int64_t n_rows, int32_t n_types, void *state, void *stream);
+
+/* Enqueues beta <- 1/K, then up to max_iter sweeps ping-ponging beta_a/beta_b (single GPU).
+ * After a stream sync, state[3] holds n_iterations and the result is in beta_a when that
+ * count is even, beta_b when odd. */
+int fdb_bcd_solve(const float *h, const float *host_gram, float *beta_a, float *beta_b,
+                  const int32_t *indptr, const int32_t *indices, int64_t n_rows, int32_t n_types,
+                  float lambda, float rho_scaled, int32_t max_iter, float tol, void *state,
+                  void *stream);
+
+/* (a10) objective pieces in float64: out[0]=sum(beta*H) out[1]=sum_i b_i^T G b_i
+ * out[2]=Tr(b^T L b) out[3]=sum|beta| out[4]=sum ysq.  Replaces compute_objective
+ * (core/solver.py:226-284) and compute_laplacian (core/spatial.py:35-73; L is never built).
+ * `out` (device, 5 doubles) is accumulated into: zero it first. */
+int fdb_objective_terms(const float *beta, const float *h, const float *ysq, const float *host_gram,
+                        const int32_t *indptr, const int32_t *indices, int64_t n_rows,
+                        int32_t n_types, double *out, void *stream);
+
+/* (a11) un-permute + widen: beta_out[order[p]][k] = beta[p][k] (float64, n x K) and the
+ * row-normalised proportions (all-zero row -> 1/K).  Replaces normalize_proportions
+ * (core/solver.py:431-452).  Either output may be NULL. */
+int fdb_finish(const float *beta, const int32_t *order, int64_t n_rows, int32_t n_types,
+               double *beta_out, double *prop_out, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (f1) gene statistics for HVG selection: per-gene sum and sum of squares of
+ * log1p(1e4 * count / max(lib_all_genes, 1)).  Replaces the O(nnz) part of select_hvg
+ * (utils/genes.py:52-83).  sums / sumsq: float64[n_genes], accumulated into (zero first).
+ * ------------------------------------------------------------------------------------- */
+int fdb_gene_moments_csr(const void *indptr, int indptr_is_int64, const int32_t *indices,
+                         const float *counts, int64_t n_spots, int32_t n_genes, double *sums,
+                         double *sumsq, void *stream);
+
+/* Multi-GPU helpers: gather / scatter whole beta rows by index list (halo exchange staging). */
+int fdb_rows_gather(const float *src, const int32_t *rows, int64_t n_list, int32_t row_floats,
+                    float *dst, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDB200_H */

@@ -1,0 +1,305 @@
+"""GPU parity suite (-m gpu): the CUDA path, called through the C ABI, against
+(1) golden fixtures = outputs of the real reference, and (2) the CPU oracle on fresh seeded inputs.
+
+Tolerances are the north star's: buckets / signs / kNN index sets bit-exact; sketched Y within
+1e-5 relative (max-abs error over max-abs value, fp32 with reordered sums); proportions within
+max-abs 1e-4 with per-type Pearson >= 0.9999 after the same number of sweeps as the reference.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+from scipy import sparse
+
+from conftest import Golden, pearson_per_type
+
+pytestmark = pytest.mark.gpu
+
+Y_REL_TOL = 1e-5
+PROP_ABS_TOL = 1e-4
+PEARSON_MIN = 0.9999
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a, dtype=np.float64) - b)) / (np.max(np.abs(b)) + 1e-300))
+
+
+def check_props(prop, ref):
+    assert prop.shape == ref.shape
+    assert np.max(np.abs(prop - ref)) <= PROP_ABS_TOL, np.max(np.abs(prop - ref))
+    assert pearson_per_type(prop, ref).min() >= PEARSON_MIN
+
+
+@pytest.fixture(scope="module")
+def fo():
+    from oracle import fd_oracle
+    return fd_oracle
+
+
+# ---------------------------------------------------------------- kernel 1/2: sketch
+def _device_sketch(g, fused):
+    import torch
+    from flashdeconv_b200 import pipeline as pl
+    from flashdeconv_b200._native import check, lib
+    tables = pl.build_tables(g.X, g.gene_idx, g.leverage, g.d, g.seed, g.Y.shape[1])
+    csr = pl.csr_to_device(g.Y)
+    n, K = g.Y.shape[0], g.X.shape[0]
+    if not fused:
+        out = torch.empty((n, g.d), dtype=torch.float32, device="cuda")
+        gb = torch.from_numpy(tables.gene_bucket).cuda()
+        gw = torch.from_numpy(tables.gene_weight).cuda()
+        check(lib.fdb_sketch_logcpm_csr(pl._ptr(csr.indptr), 1, pl._ptr(csr.indices), pl._ptr(csr.data), n,
+                                        g.Y.shape[1], pl._ptr(gb), pl._ptr(gw), g.d, pl._ptr(out),
+                                        pl._stream(torch)))
+        return out.cpu().numpy()
+    coords = torch.from_numpy(g.coords).cuda()
+    path = pl.DevicePath(csr, coords, tables, K)
+    path.stage_sketch()                 # no graph yet -> rows stay in input order
+    torch.cuda.synchronize()
+    return path.h.cpu().numpy()[:, :K], path.ysq.cpu().numpy()
+
+
+def test_sketch_matches_reference(golden):
+    Ys = _device_sketch(golden, fused=False)
+    assert rel(Ys[golden.Ys_rows], golden.Ys) <= Y_REL_TOL
+
+
+def test_fused_sketch_contract_matches_reference(golden, fo):
+    H, ysq = _device_sketch(golden, fused=True)
+    Yt, Xt = fo.log_cpm(golden.Y[:, golden.gene_idx].tocsr(), golden.X[:, golden.gene_idx])
+    Ys, Xs = fo.project(Yt, Xt, fo.omega_matrix(golden.bucket, golden.weight, golden.d))
+    assert rel(H, Ys @ Xs.T) <= Y_REL_TOL
+    assert rel(ysq, (Ys ** 2).sum(1)) <= Y_REL_TOL
+
+
+@pytest.mark.parametrize("n,G,d,density", [(1, 50, 32, 0.5), (257, 3000, 512, 0.3), (1000, 700, 64, 0.02),
+                                           (64, 40000, 128, 0.05)])
+def test_sketch_ragged_rows_vs_oracle(fo, n, G, d, density):
+    """empty rows, rows longer than the register cache (>512 nnz), unselected genes, tiny inputs"""
+    import torch
+    from flashdeconv_b200 import pipeline as pl
+    from flashdeconv_b200._native import check, lib
+    rng = np.random.default_rng(n + d)
+    Y = sparse.random(n, G, density=density, format="csr", random_state=np.random.RandomState(n),
+                      data_rvs=lambda s: rng.integers(1, 50, s).astype(np.float64))
+    if n > 3:
+        Y = sparse.vstack([Y[: n // 2], sparse.csr_matrix((1, G)), Y[n // 2 + 1:]]).tocsr()   # an empty row
+    gene_idx = np.sort(rng.choice(G, size=max(G // 3, 1), replace=False))
+    lev = rng.random(gene_idx.size)
+    bucket, _, weight = fo.countsketch_table(gene_idx.size, d, lev, 3)
+    want = fo.sketch_full_csr(Y, gene_idx, bucket, weight, d)
+    gb = np.full(G, -1, np.int32); gw = np.zeros(G, np.float32)
+    gb[gene_idx] = bucket; gw[gene_idx] = weight
+    csr = pl.csr_to_device(Y)
+    out = torch.empty((n, d), dtype=torch.float32, device="cuda")
+    check(lib.fdb_sketch_logcpm_csr(pl._ptr(csr.indptr), int(csr.indptr.dtype == torch.int64), pl._ptr(csr.indices),
+                                    pl._ptr(csr.data), n, G, pl._ptr(torch.from_numpy(gb).cuda()),
+                                    pl._ptr(torch.from_numpy(gw).cuda()), d, pl._ptr(out), pl._stream(torch)))
+    assert rel(out.cpu().numpy(), want) <= Y_REL_TOL
+
+
+def test_projection_is_linear():
+    """reference tests/test_sketching.py:95-110"""
+    from flashdeconv_b200.sketching import build_countsketch_matrix, project_to_sketch
+    rng = np.random.RandomState(42)
+    Om = build_countsketch_matrix(100, 16, random_state=42)
+    Y1, Y2, X = rng.randn(10, 100), rng.randn(10, 100), rng.randn(3, 100)
+    s1, _ = project_to_sketch(Y1, X, Om)
+    s2, _ = project_to_sketch(Y2, X, Om)
+    s12, xs = project_to_sketch(Y1 + Y2, X, Om)
+    np.testing.assert_allclose(s12, s1 + s2, rtol=1e-4, atol=1e-4)
+    assert s1.shape == (10, 16) and xs.shape == (3, 16)
+
+
+# ---------------------------------------------------------------- kernel 3: graph
+def _assert_same_graph(A, B):
+    A = sparse.csr_matrix(A); B = sparse.csr_matrix(B)
+    A.sort_indices(); B.sort_indices()
+    assert np.array_equal(A.indptr, B.indptr)
+    assert np.array_equal(A.indices, B.indices)          # bit-exact index sets
+    assert np.all(A.data == 1.0)
+
+
+def test_graph_matches_reference(golden):
+    from flashdeconv_b200.graph import coords_to_adjacency
+    _assert_same_graph(coords_to_adjacency(golden.coords, method=golden.method, k=golden.k), golden.A)
+
+
+@pytest.mark.parametrize("n,k", [(2, 6), (5, 6), (7, 6), (100, 1), (1000, 4), (5000, 6), (20000, 10), (3000, 20)])
+def test_knn_vs_oracle_random_points(fo, n, k):
+    from flashdeconv_b200.graph import build_knn_graph
+    rng = np.random.default_rng(n * 31 + k)
+    coords = rng.random((n, 2)) * np.array([100.0, 37.0])
+    _assert_same_graph(build_knn_graph(coords, k=k), fo.knn_adjacency(coords, k))
+
+
+def test_knn_clustered_and_elongated(fo):
+    from flashdeconv_b200.graph import build_knn_graph
+    rng = np.random.default_rng(3)
+    blobs = np.concatenate([rng.normal(c, 0.01, size=(400, 2)) for c in ((0, 0), (5, 5), (9, 0.5))])
+    _assert_same_graph(build_knn_graph(blobs, k=6), fo.knn_adjacency(blobs, 6))
+    line = np.column_stack([np.sort(rng.random(2000)) * 1e4, rng.random(2000) * 1e-3])
+    _assert_same_graph(build_knn_graph(line, k=6), fo.knn_adjacency(line, 6))
+
+
+def test_knn_properties_and_degenerate():
+    """reference tests/test_spatial.py:22-51 + k clamp (graph.py:51)"""
+    from flashdeconv_b200.graph import build_knn_graph, coords_to_adjacency
+    rng = np.random.RandomState(42)
+    c = rng.rand(50, 2)
+    A = build_knn_graph(c, k=5)
+    assert A.shape == (50, 50) and (A != A.T).nnz == 0 and A.diagonal().sum() == 0
+    assert build_knn_graph(c, k=5, include_self=True).diagonal().sum() == 50
+    assert build_knn_graph(c[:1], k=5).nnz == 0
+    assert build_knn_graph(c, k=0).nnz == 0
+    assert build_knn_graph(c[:4], k=6).nnz == 12           # complete graph on 4 points
+    for m, kw in (("knn", dict(k=4)), ("radius", dict(radius=0.3)), ("grid", {})):
+        assert coords_to_adjacency(c, method=m, **kw).shape == (50, 50)
+    with pytest.raises(ValueError, match="Unknown method"):
+        coords_to_adjacency(c, method="nope")
+
+
+def test_radius_graph_known_answers(fo):
+    """reference tests/test_spatial.py:57-86"""
+    from flashdeconv_b200.graph import build_grid_graph, build_radius_graph
+    grid = np.array([[i, j] for i in range(3) for j in range(3)], dtype=float)
+    assert build_radius_graph(grid, 1.5)[4].nnz == 8
+    assert build_radius_graph(grid, 1.1)[4].nnz == 4
+    far = np.array([[0.0, 0.0], [10.0, 10.0]])
+    assert build_radius_graph(far, 1.0).nnz == 0
+    assert build_radius_graph(far, 1.0, include_self=True).diagonal().sum() == 2
+    rng = np.random.default_rng(0)
+    pts = rng.random((3000, 2)) * 50
+    _assert_same_graph(build_radius_graph(pts, 1.7), fo.radius_adjacency(pts, 1.7))
+    side = 70
+    lattice = np.column_stack([np.tile(np.arange(side), side), np.repeat(np.arange(side), side)]).astype(float)
+    _assert_same_graph(build_grid_graph(lattice), fo.grid_adjacency(lattice))
+    hexa = lattice.copy(); hexa[:, 0] += 0.5 * (hexa[:, 1] % 2); hexa[:, 1] *= np.sqrt(3) / 2
+    _assert_same_graph(build_grid_graph(hexa[:4899]), fo.grid_adjacency(hexa[:4899]))   # odd count -> plain median
+
+
+# ---------------------------------------------------------------- kernel 4: solver
+def test_bcd_solve_matches_reference(golden):
+    from flashdeconv_b200.solver import bcd_solve, normalize_proportions
+    Yt_full = None
+    from oracle import fd_oracle as fo
+    Yt, Xt = fo.log_cpm(golden.Y[:, golden.gene_idx].tocsr(), golden.X[:, golden.gene_idx])
+    Ys, Xs = fo.project(Yt, Xt, fo.omega_matrix(golden.bucket, golden.weight, golden.d))
+    beta, info = bcd_solve(Ys, Xs, golden.A, lambda_=golden.lam, rho=0.01, max_iter=golden.max_iter, tol=1e-4)
+    assert info["n_iterations"] == golden.n_iterations and info["converged"] == golden.converged
+    assert beta.min() >= 0.0
+    check_props(normalize_proportions(beta), golden.proportions)
+    assert np.max(np.abs(beta - golden.beta)) <= 1e-4 * max(1.0, np.abs(golden.beta).max())
+    assert abs(info["final_objective"] - golden.final_objective) <= 1e-4 * abs(golden.final_objective)
+    assert abs(info["final_change"] - golden.final_change) <= 0.05 * golden.final_change + 1e-6
+
+
+def test_bcd_solver_fixtures_from_reference_tests():
+    """tests/test_solver.py:67-147 and :295-321 shapes, incl. early convergence + determinism hash"""
+    import os
+    from conftest import ROOT
+    from flashdeconv_b200.solver import bcd_solve
+    z = np.load(os.path.join(ROOT, "tests", "golden", "solver_fixtures.npz"))
+    for tag in ("simple", "determinism"):
+        n = len(z[f"{tag}_A_indptr"]) - 1
+        A = sparse.csr_matrix((np.ones(len(z[f"{tag}_A_indices"])), z[f"{tag}_A_indices"], z[f"{tag}_A_indptr"]),
+                              shape=(n, n))
+        lam, rho, max_iter, tol = z[f"{tag}_kw"]
+        b1, i1 = bcd_solve(z[f"{tag}_Ys"], z[f"{tag}_Xs"], A, lam, rho, int(max_iter), tol)
+        b2, i2 = bcd_solve(z[f"{tag}_Ys"], z[f"{tag}_Xs"], A, lam, rho, int(max_iter), tol)
+        assert hashlib.sha256(b1.tobytes()).hexdigest() == hashlib.sha256(b2.tobytes()).hexdigest()
+        assert i1["n_iterations"] == i2["n_iterations"] and i1["converged"] == i2["converged"]
+        assert set(i1) == {"converged", "n_iterations", "final_objective", "objectives", "final_change"}
+        assert b1.shape == z[f"{tag}_beta"].shape and b1.min() >= -1e-10
+        assert np.max(np.abs(b1 - z[f"{tag}_beta"])) < 2e-3        # stops within a sweep of the reference
+        assert abs(i1["n_iterations"] - int(z[f"{tag}_n_iterations"])) <= 1
+        assert i1["converged"] == bool(z[f"{tag}_converged"])
+
+
+@pytest.mark.parametrize("K", [1, 3, 4, 9, 17, 33, 50, 64])
+def test_bcd_all_type_counts_vs_oracle(fo, K):
+    """every Kp instantiation of the sweep kernel, isolated spots (deg 0) included"""
+    from flashdeconv_b200.solver import bcd_solve
+    rng = np.random.default_rng(K)
+    n, d = 700, 96
+    Xs = rng.standard_normal((K, d)) + 0.3
+    bt = rng.random((n, K)) * (rng.random((n, K)) < 0.4)
+    Ys = bt @ Xs + 0.05 * rng.standard_normal((n, d))
+    coords = rng.random((n, 2))
+    A = fo.radius_adjacency(coords, 0.03)                       # sparse graph with isolated spots
+    assert (np.diff(A.indptr) == 0).any()
+    want, winfo = fo.bcd_solve(Ys, Xs, A, 2.0, 0.01, 25, 1e-9)
+    got, info = bcd_solve(Ys, Xs, A, lambda_=2.0, rho=0.01, max_iter=25, tol=1e-9)
+    assert info["n_iterations"] == winfo["n_iterations"] == 25
+    assert np.max(np.abs(got - want)) <= 2e-4 * max(1.0, np.abs(want).max())
+    assert abs(info["final_objective"] - winfo["final_objective"]) <= 1e-4 * abs(winfo["final_objective"]) + 1e-3
+
+
+def test_bcd_edge_cases():
+    from flashdeconv_b200.solver import bcd_solve, normalize_proportions, compute_objective
+    from flashdeconv_b200.spatial import compute_laplacian
+    from flashdeconv_b200.graph import build_knn_graph
+    rng = np.random.default_rng(0)
+    Xs, Ys = rng.standard_normal((5, 32)), rng.standard_normal((40, 32))
+    A = build_knn_graph(rng.random((40, 2)), k=4)
+    b0, i0 = bcd_solve(Ys, Xs, A, max_iter=0)
+    assert i0["n_iterations"] == 0 and i0["final_change"] == 0.0 and not i0["converged"]
+    assert np.allclose(b0, 0.2)
+    be, ie = bcd_solve(np.empty((0, 32)), Xs, sparse.csr_matrix((0, 0)))
+    assert be.shape == (0, 5) and ie["converged"] and ie["n_iterations"] == 0
+    bv, iv = bcd_solve(Ys, Xs, A, lambda_=0.1, rho=0.01, max_iter=12, verbose=True)
+    assert len(iv["objectives"]) >= 2 and all(np.isfinite(iv["objectives"]))
+    p = normalize_proportions(np.array([[1.0, 2.0, 3.0], [0.0, 0.0, 0.0], [2.0, 2.0, 0.0]]))
+    np.testing.assert_allclose(p, [[1 / 6, 1 / 3, .5], [1 / 3, 1 / 3, 1 / 3], [.5, .5, 0.0]], rtol=1e-6)
+    beta = rng.random((40, 5))
+    Yfit = beta @ Xs
+    L = compute_laplacian(A)
+    H = Xs @ Yfit.T
+    obj = compute_objective(beta, H, Xs @ Xs.T, float(np.sum(Yfit ** 2)), L, 0.0, 0.0)
+    assert abs(obj) < 1e-2 * float(np.sum(Yfit ** 2)) * 1e-3          # ~0 at a perfect fit (fp32 H)
+    want = (0.5 * np.sum((Ys - beta @ Xs) ** 2) + 0.5 * 0.7 * np.sum(beta * (L @ beta)) + 0.3 * np.abs(beta).sum())
+    got = compute_objective(beta, Xs @ Ys.T, Xs @ Xs.T, float(np.sum(Ys ** 2)), L, 0.7, 0.3)
+    assert abs(got - want) <= 1e-5 * abs(want)
+
+
+# ---------------------------------------------------------------- the whole path behind the public API
+def test_fit_transform_matches_reference(golden):
+    from flashdeconv_b200 import FlashDeconv
+    m = FlashDeconv(sketch_dim=golden.d, k_neighbors=golden.k, spatial_method=golden.method,
+                    max_iter=golden.max_iter, n_hvg=golden.n_hvg, n_markers_per_type=golden.n_markers,
+                    random_state=golden.seed)
+    prop = m.fit_transform(golden.Y_input(), golden.X, golden.coords)
+    assert np.array_equal(m.gene_idx_, golden.gene_idx)
+    assert prop.dtype == np.float64 and m.beta_.dtype == np.float64
+    check_props(prop, golden.proportions)
+    assert m.info_["n_iterations"] == golden.n_iterations and m.info_["converged"] == golden.converged
+    assert abs(m.lambda_used_ - golden.lam) <= 1e-9 * golden.lam
+    assert abs(m.info_["final_objective"] - golden.final_objective) <= 1e-4 * abs(golden.final_objective)
+    _assert_same_graph(m.adjacency_, golden.A)
+    np.testing.assert_allclose(prop.sum(1), 1.0, atol=1e-9)
+    assert m.summary()["fitted"] and m.get_dominant_cell_type().shape == (golden.Y.shape[0],)
+
+
+def test_fit_variants_behave_like_the_reference_tests():
+    """tests/test_integration.py:117-271: sparse==dense input, seeds, sketch dims, radius/grid methods"""
+    from flashdeconv_b200 import FlashDeconv
+    from flashdeconv_b200.synth import make_dataset
+    ds = make_dataset(n_spots=100, n_genes=500, n_types=5, depth=5000.0, seed=42)
+    Yd = ds.Y.toarray()
+    p_dense = FlashDeconv(sketch_dim=64, max_iter=50).fit_transform(Yd, ds.X, ds.coords)
+    p_sparse = FlashDeconv(sketch_dim=64, max_iter=50).fit_transform(ds.Y, ds.X, ds.coords)
+    assert p_dense.shape == (100, 5) and np.all(p_dense >= 0)
+    np.testing.assert_allclose(p_dense, p_sparse, atol=1e-6)
+    p_again = FlashDeconv(sketch_dim=64, max_iter=50, random_state=0).fit_transform(Yd, ds.X, ds.coords)
+    assert np.array_equal(p_dense, p_again)                     # bitwise reproducible
+    for d in (32, 64, 128):
+        assert FlashDeconv(sketch_dim=d, max_iter=20).fit_transform(Yd, ds.X, ds.coords).shape == (100, 5)
+    corr = np.corrcoef(p_dense.ravel(), ds.beta_true.ravel())[0, 1]
+    assert corr > 0.3
+    for kw in (dict(spatial_method="radius", radius=2.0), dict(spatial_method="grid")):
+        m = FlashDeconv(sketch_dim=64, max_iter=20, **kw).fit(Yd, ds.X, ds.coords)
+        np.testing.assert_allclose(m.proportions_.sum(1), 1.0, atol=1e-9)
+    m = FlashDeconv(sketch_dim=64, lambda_spatial=0.5, max_iter=5).fit(Yd, ds.X, ds.coords)
+    assert m.lambda_used_ == 0.5 and m.info_["n_iterations"] == 5
+    with pytest.raises(NotImplementedError):
+        FlashDeconv(preprocess="pearson").fit(Yd, ds.X, ds.coords)

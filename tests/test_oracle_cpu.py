@@ -1,0 +1,183 @@
+"""CPU suite: the oracle against the golden fixtures (outputs of the real reference), the
+host-side logic of the package, and the C-ABI surface (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+from scipy import sparse
+
+from conftest import ROOT, Golden, PATH_CASES
+from oracle import fd_oracle as fo
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / (np.max(np.abs(b)) + 1e-300))
+
+
+# ------------------------------------------------------------------ oracle vs reference goldens
+def test_oracle_gene_selection_matches_reference(golden):
+    idx, lev = fo.select_genes(golden.Y_input(), golden.X, golden.n_hvg, golden.n_markers)
+    assert np.array_equal(idx, golden.gene_idx)
+    assert rel(lev, golden.leverage) < 1e-9
+
+
+def test_oracle_countsketch_bit_exact(golden):
+    bucket, sign, weight = fo.countsketch_table(len(golden.gene_idx), golden.d, golden.leverage, golden.seed)
+    assert np.array_equal(bucket, golden.bucket)
+    assert np.array_equal(sign, np.sign(golden.weight).astype(np.int64))
+    assert rel(weight, golden.weight) < 1e-12
+
+
+def test_oracle_path_matches_reference(golden):
+    res = fo.run_path(golden.Y_input(), golden.X, golden.coords, golden.gene_idx, golden.leverage, d=golden.d,
+                      method=golden.method, k=golden.k, max_iter=golden.max_iter, seed=golden.seed)
+    assert rel(res["Y_s"][golden.Ys_rows], golden.Ys) < 1e-12
+    assert rel(res["X_s"], golden.Xs) < 1e-12
+    A = res["A"].tocsr()
+    A.sort_indices()
+    assert np.array_equal(A.indptr, golden.A.indptr) and np.array_equal(A.indices, golden.A.indices)
+    assert abs(res["lam"] - golden.lam) <= 1e-12 * golden.lam
+    assert res["info"]["n_iterations"] == golden.n_iterations
+    assert res["info"]["converged"] == golden.converged
+    assert rel(res["beta"], golden.beta) < 1e-9
+    assert rel(res["proportions"], golden.proportions) < 1e-9
+    assert abs(res["info"]["final_objective"] - golden.final_objective) <= 1e-9 * abs(golden.final_objective)
+    assert abs(res["info"]["final_change"] - golden.final_change) <= 1e-6 * abs(golden.final_change)
+
+
+def test_oracle_fused_csr_sketch_equals_staged():
+    g = Golden("path_sparse_k30")
+    Yf = fo.sketch_full_csr(g.Y, g.gene_idx, g.bucket, g.weight, g.d)
+    assert rel(Yf[g.Ys_rows], g.Ys) < 1e-12
+
+
+def test_oracle_solver_fixtures():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "solver_fixtures.npz"))
+    for tag in ("simple", "determinism"):
+        n = len(z[f"{tag}_A_indptr"]) - 1
+        A = sparse.csr_matrix((np.ones(len(z[f"{tag}_A_indices"])), z[f"{tag}_A_indices"], z[f"{tag}_A_indptr"]),
+                              shape=(n, n))
+        lam, rho, max_iter, tol = z[f"{tag}_kw"]
+        beta, info = fo.bcd_solve(z[f"{tag}_Ys"], z[f"{tag}_Xs"], A, lam, rho, int(max_iter), tol)
+        assert rel(beta, z[f"{tag}_beta"]) < 1e-9
+        assert info["n_iterations"] == int(z[f"{tag}_n_iterations"])
+        assert info["converged"] == bool(z[f"{tag}_converged"])
+        Ak = fo.knn_adjacency(z[f"{tag}_coords"], 4)
+        Ak.sort_indices()
+        assert np.array_equal(Ak.indices, z[f"{tag}_A_indices"])
+
+
+def test_oracle_known_answers():
+    b = np.array([[1.0, 2.0, 3.0], [0.0, 0.0, 0.0], [2.0, 2.0, 0.0]])
+    p = fo.normalize(b)
+    assert np.allclose(p[0], [1 / 6, 2 / 6, 3 / 6]) and np.allclose(p[1], 1 / 3) and np.allclose(p[2], [.5, .5, 0])
+    grid = np.array([[i, j] for i in range(3) for j in range(3)], dtype=float)
+    assert fo.radius_adjacency(grid, 1.5)[4].nnz == 8 and fo.radius_adjacency(grid, 1.1)[4].nnz == 4
+    rng = np.random.default_rng(0)
+    c = rng.random((200, 2))
+    A = fo.knn_adjacency(c, 5)
+    assert (A != A.T).nnz == 0 and A.diagonal().sum() == 0
+    nn = fo.knn_directed_bruteforce(c, 5)
+    D = sparse.csr_matrix((np.ones(nn.size), (np.repeat(np.arange(200), 5), nn.ravel())), shape=(200, 200))
+    S = ((D + D.T) > 0).astype(float)
+    assert (S != A).nnz == 0
+
+
+def test_oracle_objective_zero_at_perfect_fit():
+    rng = np.random.default_rng(1)
+    Xs = rng.standard_normal((4, 16))
+    beta = rng.random((30, 4))
+    Ys = beta @ Xs
+    A = fo.knn_adjacency(rng.random((30, 2)), 3)
+    H = (Xs @ Ys.T).T
+    assert abs(fo.objective(beta, H, Xs @ Xs.T, float(np.sum(Ys ** 2)), A, 0.0, 0.0)) < 1e-8
+
+
+# ------------------------------------------------------------------ host logic of the package
+def test_package_gene_selection_matches_reference(golden):
+    from flashdeconv_b200 import genes
+    idx, lev = genes.select_informative_genes(golden.Y_input(), golden.X, golden.n_hvg, golden.n_markers)
+    assert np.array_equal(idx, golden.gene_idx)
+    assert rel(lev, golden.leverage) < 1e-9
+
+
+def test_package_tables_bit_exact(golden):
+    from flashdeconv_b200.pipeline import build_tables
+    t = build_tables(golden.X, golden.gene_idx, golden.leverage, golden.d, golden.seed, golden.Y.shape[1])
+    assert np.array_equal(t.bucket, golden.bucket)                       # buckets bit-exact
+    assert np.array_equal(t.sign, np.sign(golden.weight).astype(np.int64))   # signs bit-exact
+    assert rel(t.weight, golden.weight) < 1e-12
+    assert rel(t.X_sketch, golden.Xs) < 1e-12
+    sel = t.gene_bucket >= 0
+    assert np.array_equal(np.flatnonzero(sel), golden.gene_idx)
+    assert np.array_equal(t.gene_bucket[sel], golden.bucket.astype(np.int32))
+
+
+def test_countsketch_matrix_properties():
+    """reference tests/test_sketching.py:16-51: shape, one entry per row, same seed -> identical."""
+    from flashdeconv_b200.sketching import build_countsketch_matrix
+    Om = build_countsketch_matrix(100, 16, random_state=42)
+    assert Om.shape == (100, 16)
+    assert np.all(np.diff(Om.tocsr().indptr) == 1)
+    Om2 = build_countsketch_matrix(100, 16, random_state=42)
+    assert np.array_equal(Om.toarray(), Om2.toarray())
+    lev = np.random.RandomState(0).rand(100)
+    assert build_countsketch_matrix(100, 16, leverage_scores=lev / lev.sum(), random_state=42).shape == (100, 16)
+
+
+def test_estimator_validation_messages():
+    """reference core/deconv.py:105-124 and tests/test_integration.py:254-257,387-422."""
+    from flashdeconv_b200 import FlashDeconv
+    with pytest.raises(ValueError, match="radius must be specified"):
+        FlashDeconv(spatial_method="radius")
+    with pytest.raises(ValueError, match="sketch_dim must be positive"):
+        FlashDeconv(sketch_dim=0)
+    with pytest.raises(ValueError, match="tol must be positive"):
+        FlashDeconv(tol=0)
+    m = FlashDeconv()
+    with pytest.raises(RuntimeError, match="not been fitted"):
+        m.get_cell_type_proportions()
+    assert m.summary() == {"fitted": False}
+    Y, X, c = np.ones((5, 7)), np.ones((2, 6)), np.zeros((5, 2))
+    with pytest.raises(ValueError, match="Gene dimension mismatch"):
+        m.fit(Y, X, c)
+    with pytest.raises(ValueError, match="Spot count mismatch"):
+        m.fit(Y, np.ones((2, 7)), np.zeros((4, 2)))
+    with pytest.raises(ValueError, match="at least one cell type"):
+        m.fit(Y, np.ones((0, 7)), c)
+    assert "not fitted" in repr(m)
+
+
+def test_synth_generator_is_deterministic():
+    from flashdeconv_b200.synth import make_dataset
+    a = make_dataset(300, 200, 4, depth=100.0, seed=5)
+    b = make_dataset(300, 200, 4, depth=100.0, seed=5)
+    assert np.array_equal(a.Y.indices, b.Y.indices) and np.array_equal(a.Y.data, b.Y.data)
+    assert np.array_equal(a.coords, b.coords) and a.Y.shape == (300, 200)
+    assert np.allclose(a.beta_true.sum(1), 1.0)
+
+
+# ------------------------------------------------------------------ C-ABI surface
+def test_cabi_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "fdb200.h")).read()
+    declared = set(re.findall(r"\b(fdb_[a-z0-9_]+)\s*\(", header))
+    declared -= {"fdb_status"}
+    assert len(declared) >= 15
+    from flashdeconv_b200 import _native
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    so = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(so, name), name
+    assert _native.lib.fdb_abi_version() == 1
+    assert [_native.padded_types(k) for k in (1, 4, 5, 30, 50, 64)] == [4, 4, 8, 32, 52, 64]
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "flashdeconv_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "fd_oracle" not in src and "import oracle" not in src and "from oracle" not in src, f
