@@ -18,6 +18,7 @@ SIGNATURES = {
     "fdb_abi_version": (C.c_int, []),
     "fdb_last_error": (C.c_char_p, []),
     "fdb_padded_types": (C.c_int, [C.c_int]),
+    "fdb_launch_count": (C.c_longlong, []),
     "fdb_sketch_logcpm_csr": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp]),
     "fdb_sketch_project_csr": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _vp]),
     "fdb_contract": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),

@@ -479,6 +479,7 @@ extern "C" __attribute__((visibility("default"))) int fdb_objective_terms(const 
         objective_kernel<1><<<grid, 256, smem, st>>>(beta, h, ysq, gram_pad, indptr, indices, n_rows, kp, out);
     else
         objective_kernel<2><<<grid, 256, smem, st>>>(beta, h, ysq, gram_pad, indptr, indices, n_rows, kp, out);
+    count_launches(1);
     FDB_LAUNCH_CHECK("objective_kernel");
     FDB_CUDA(cudaFreeAsync(gram_dev, st));
     return FDB_OK;

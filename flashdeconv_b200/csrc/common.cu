@@ -4,6 +4,7 @@
 
 namespace fdb {
 static thread_local char g_err[512] = "";
+long long g_launches = 0;
 
 void set_error(const char *fmt, ...)
 {
@@ -23,4 +24,5 @@ int cuda_fail(cudaError_t e, const char *what)
 #define FDB_API extern "C" __attribute__((visibility("default")))
 FDB_API int fdb_abi_version(void) { return 1; }
 FDB_API const char *fdb_last_error(void) { return fdb::g_err; }
+FDB_API long long fdb_launch_count(void) { return fdb::g_launches; }
 FDB_API int fdb_padded_types(int n_types) { return n_types <= 0 ? 0 : (int)fdb::round_up(n_types, 4); }

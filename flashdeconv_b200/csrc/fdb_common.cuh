@@ -24,8 +24,11 @@ int cuda_fail(cudaError_t e, const char *what);
         if (e__ != cudaSuccess) return fdb::cuda_fail(e__, #call);            \
     } while (0)
 
+extern long long g_launches;      // kernels launched through this library (bench.py's gpu_launches)
+
 #define FDB_LAUNCH_CHECK(name)                                                \
     do {                                                                      \
+        ++fdb::g_launches;                                                    \
         cudaError_t e__ = cudaGetLastError();                                 \
         if (e__ != cudaSuccess) return fdb::cuda_fail(e__, name);             \
     } while (0)
@@ -37,6 +40,8 @@ int cuda_fail(cudaError_t e, const char *what);
             return FDB_ERR_ARG;                                               \
         }                                                                     \
     } while (0)
+
+inline void count_launches(int n) { g_launches += n; }
 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }

@@ -194,6 +194,7 @@ static int exclusive_scan(const int32_t *in, int64_t n, int32_t *out, int32_t *b
     scan_reduce_kernel<<<n_blocks, kScanThreads, 0, st>>>(in, n, block_sums);
     scan_block_sums_kernel<<<1, 1024, 0, st>>>(block_sums, n_blocks, out + n);
     scan_apply_kernel<<<n_blocks, kScanThreads, 0, st>>>(in, n, block_sums, out);
+    count_launches(2);
     FDB_LAUNCH_CHECK("exclusive_scan");
     return FDB_OK;
 }
@@ -579,6 +580,7 @@ static int bin_spots(const double *coords, int64_t n, const GridSpec &g, const s
     if (rc) return rc;
     cell_scatter_kernel<<<grid1d(n, 256), 256, 0, st>>>(s.cell_of, n, s.hist, s.cursor, order);
     cell_finish_kernel<<<grid1d(g.n_cells, 256), 256, 0, st>>>(coords, g.n_cells, s.hist, order, rank, s.xy);
+    count_launches(2);
     FDB_LAUNCH_CHECK("bin_spots");
     return FDB_OK;
 }
@@ -695,6 +697,7 @@ extern "C" __attribute__((visibility("default"))) int fdb_graph_build(const doub
         FDB_CUDA(cudaMemsetAsync(s.extra, 0, (n + 1) * 4, st));
         reverse_count_kernel<<<grid1d(n * k_eff, 256), 256, 0, st>>>(s.knn, n, k_eff, s.extra);
         degree_kernel<<<grid1d(n, 256), 256, 0, st>>>(s.knn, s.extra, n, k_eff, s.deg);
+        count_launches(1);
         FDB_LAUNCH_CHECK("degree_kernel");
     } else {
         radius_kernel<false><<<grid1d(n, 128), 128, 0, st>>>(s.xy, n, g, s.tile_rank, s.hist, r2, s.deg, nullptr, nullptr);
@@ -717,6 +720,7 @@ extern "C" __attribute__((visibility("default"))) int fdb_graph_build(const doub
         radius_kernel<true><<<grid1d(n, 128), 128, 0, st>>>(s.xy, n, g, s.tile_rank, s.hist, r2, nullptr, indptr, indices);
     }
     row_sort_kernel<<<grid1d(n, 256), 256, 0, st>>>(indptr, n, indices);
+    count_launches(1);
     FDB_LAUNCH_CHECK("graph fill");
     return FDB_OK;
 }
@@ -743,6 +747,7 @@ extern "C" __attribute__((visibility("default"))) int fdb_graph_to_input_order(c
     int rc = exclusive_scan(deg, n, out_indptr, block_sums, st);
     if (rc) return rc;
     input_fill_kernel<<<grid1d(n, 256), 256, 0, st>>>(indptr, indices, order, rank, n, out_indptr, out_indices);
+    count_launches(1);
     FDB_LAUNCH_CHECK("input_fill_kernel");
     return FDB_OK;
 }

@@ -103,14 +103,12 @@ class FlashDeconv:
 
         torch = pipeline._native.require_cuda()
         say(f"Step 2-3: log-CPM + sketching to {self.sketch_dim} dimensions (fused, on device)...")
-        tables = pipeline.build_tables(X, gene_idx, leverage, self.sketch_dim, self.random_state, Y.shape[1])
-        csr = pipeline.csr_to_device(Y)
-        coords_dev = torch.from_numpy(np.ascontiguousarray(coords, dtype=np.float64)).to(csr.indices.device)
-        path = pipeline.DevicePath(csr, coords_dev, tables, X.shape[0])
         say("Step 4-6: spatial graph, lambda, block coordinate descent...")
-        res = path.run(method=self.spatial_method, k=self.k_neighbors, radius=self.radius,
-                       lam=self.lambda_spatial, rho=self.rho_sparsity, max_iter=self.max_iter, tol=self.tol,
-                       verbose=self.verbose)
+        res = pipeline.deconvolve_path(Y, X, coords, gene_idx, leverage, sketch_dim=self.sketch_dim,
+                                       lambda_spatial=self.lambda_spatial, rho_sparsity=self.rho_sparsity,
+                                       spatial_method=self.spatial_method, k_neighbors=self.k_neighbors,
+                                       radius=self.radius, max_iter=self.max_iter, tol=self.tol,
+                                       random_state=self.random_state, verbose=self.verbose)
         self._graph, self._adjacency = res.graph, None
         self.lambda_used_ = res.lambda_used
         self.beta_, self.proportions_, self.info_ = res.beta, res.proportions, res.info

@@ -44,11 +44,24 @@ class DeviceCSR:
         return int(self.indices.numel())
 
 
+@dataclass
+class HostCSR:
+    """CSR arrays already laid out for the device (pinned torch CPU tensors): skips scipy normalisation."""
+    indptr: "object"
+    indices: "object"
+    data: "object"
+    shape: tuple
+
+
 def csr_to_device(Y, device="cuda", non_blocking=True) -> DeviceCSR:
-    """Accepts a scipy sparse matrix, a dense ndarray (converted to CSR on the host) or a DeviceCSR."""
+    """Accepts a scipy sparse matrix, a dense ndarray (converted to CSR on the host), a HostCSR or a DeviceCSR."""
     torch = _native.require_cuda()
     if isinstance(Y, DeviceCSR):
         return Y
+    if isinstance(Y, HostCSR):
+        dev = torch.device(device)
+        return DeviceCSR(Y.indptr.to(dev, non_blocking=True), Y.indices.to(dev, non_blocking=True),
+                         Y.data.to(dev, non_blocking=True), tuple(Y.shape))
     if not sparse.issparse(Y):
         Y = sparse.csr_matrix(np.asarray(Y))
     Y = Y.tocsr()
@@ -281,6 +294,41 @@ class DevicePath:
         return b64.cpu().numpy(), p64.cpu().numpy()
 
     # ---- whole path -------------------------------------------------------------------
+    def run_resident(self, *, method="knn", k=6, radius=None, lam="auto", rho=0.01, max_iter=100, tol=1e-4,
+                     events=None):
+        """Hot path with inputs and outputs resident in HBM (what bench.py's `value` times): graph, fused
+        sketch, BCD sweeps, objective, float64 beta / proportions in input order.  Returns device tensors.
+        ``events``: optional dict that receives (start, end) CUDA-event pairs per stage."""
+        t = self.torch
+        n = self.csr.shape[0]
+
+        def mark(name, fn):
+            if events is None:
+                return fn()
+            a, b = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            a.record()
+            out = fn()
+            b.record()
+            events[name] = (a, b)
+            return out
+
+        mark("graph", lambda: self.stage_graph(method, k, radius))
+        mark("sketch", self.stage_sketch)
+        lam_used = self.lambda_auto() if isinstance(lam, str) else float(lam)
+        rho_s = self.rho_scaled(rho)
+        mark("solve", lambda: self.stage_solve(lam_used, rho_s, max_iter, tol))
+        n_iter, conv, rel = self.read_state()
+        beta_dev = self.current_beta(n_iter)
+        obj = mark("objective", lambda: self.objective(beta_dev, lam_used, rho_s)) if n else 0.0
+        if not hasattr(self, "_b64"):
+            self._b64 = t.empty((n, self.K), dtype=t.float64, device=self.dev)
+            self._p64 = t.empty((n, self.K), dtype=t.float64, device=self.dev)
+        mark("finish", lambda: check(lib.fdb_finish(_ptr(beta_dev), _ptr(self.graph.order), n, self.K,
+                                                    _ptr(self._b64), _ptr(self._p64), _stream(t)), "finish"))
+        info = dict(converged=conv, n_iterations=n_iter, final_objective=obj, objectives=[],
+                    final_change=rel if max_iter else 0.0)
+        return self._b64, self._p64, info, lam_used
+
     def run(self, *, method="knn", k=6, radius=None, lam="auto", rho=0.01, max_iter=100, tol=1e-4,
             verbose=False, pinned_out=False) -> SolveResult:
         t = self.torch
@@ -337,3 +385,19 @@ def gene_moments(csr: DeviceCSR):
                                    _ptr(csr.data), csr.shape[0], G, _ptr(sums), _ptr(sq), _stream(torch)),
           "gene_moments_csr")
     return sums.cpu().numpy(), sq.cpu().numpy()
+
+
+def deconvolve_path(Y, X, coords, gene_idx, leverage, *, sketch_dim=512, lambda_spatial="auto", rho_sparsity=0.01,
+                    spatial_method="knn", k_neighbors=6, radius=None, max_iter=100, tol=1e-4, random_state=0,
+                    verbose=False, pinned_out=False) -> SolveResult:
+    """Steps 2-6 of FlashDeconv.fit for HOST inputs (scipy CSR / ndarray counts, ndarray coords): uploads,
+    runs the device path, downloads float64 beta / proportions in input order.  This is the call
+    `FlashDeconv.fit` makes after gene selection and the one bench.py times end to end."""
+    torch = _native.require_cuda()
+    tables = build_tables(X, gene_idx, leverage, sketch_dim, random_state, Y.shape[1])
+    csr = csr_to_device(Y)
+    c = coords if torch.is_tensor(coords) else torch.from_numpy(np.ascontiguousarray(coords, dtype=np.float64))
+    coords_dev = c.to(csr.indices.device, non_blocking=True)
+    path = DevicePath(csr, coords_dev, tables, np.asarray(X).shape[0])
+    return path.run(method=spatial_method, k=k_neighbors, radius=radius, lam=lambda_spatial, rho=rho_sparsity,
+                    max_iter=max_iter, tol=tol, verbose=verbose, pinned_out=pinned_out)

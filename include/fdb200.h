@@ -46,6 +46,7 @@ typedef enum {
 int fdb_abi_version(void);
 const char *fdb_last_error(void);
 int fdb_padded_types(int n_types);                       /* Kp */
+long long fdb_launch_count(void);                        /* kernels launched by this library so far */
 
 /* ---------------------------------------------------------------------------------------
  * (a1 + a3) log-CPM fused with the leverage-weighted CountSketch, one pass over the FULL
