@@ -124,6 +124,7 @@ def main():
     ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="spots in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -219,12 +220,15 @@ def main():
     del path
     torch.cuda.empty_cache()
     e2e_times = []
-    for it in range(2 + min(args.steps, 3)):
+    for it in range(0 if args.no_e2e else 2 + min(args.steps, 3)):
         barrier()
         t0 = time.perf_counter()
         res = pipeline.deconvolve_path(host, data["X"], data["host_coords"], gene_idx, leverage, **e2e_kw)
         torch.cuda.synchronize()
         e2e_times.append(time.perf_counter() - t0)
+    if args.no_e2e:
+        res = pipeline.deconvolve_path(host, data["X"], data["host_coords"], gene_idx, leverage, **e2e_kw)
+        e2e_times = [float("nan")] * 3
     e2e_s = float(np.mean(e2e_times[2:]))
     if distributed:
         tt = torch.tensor([e2e_s], device="cuda")

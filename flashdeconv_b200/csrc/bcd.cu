@@ -284,14 +284,18 @@ static int dispatch_sweep(const float *h, const float *host_gram, int n_types, c
 // ------------------------------------------------------------------------------------
 // objective terms (float64 accumulation), warp per spot
 // ------------------------------------------------------------------------------------
+struct GramFull {
+    float g[FDB_MAX_TYPES * FDB_MAX_TYPES];               // kp x kp row-major in the first kp*kp entries
+};
+
 template <int NK>
 __global__ void __launch_bounds__(256)
 objective_kernel(const float *__restrict__ beta, const float *__restrict__ h, const float *__restrict__ ysq,
-                 const float *__restrict__ gram_padded, const int32_t *__restrict__ indptr,
+                 const __grid_constant__ GramFull gram, const int32_t *__restrict__ indptr,
                  const int32_t *__restrict__ indices, int64_t n_rows, int kp, double *__restrict__ out)
 {
     extern __shared__ float gs[];                          // kp x kp
-    for (int i = threadIdx.x; i < kp * kp; i += blockDim.x) gs[i] = gram_padded[i];
+    for (int i = threadIdx.x; i < kp * kp; i += blockDim.x) gs[i] = gram.g[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -345,14 +349,6 @@ objective_kernel(const float *__restrict__ beta, const float *__restrict__ h, co
         double t = 0.0;
         for (int w = 0; w < 8; ++w) t += red[threadIdx.x][w];
         atomicAdd(out + threadIdx.x, t);
-    }
-}
-
-__global__ void pad_gram_kernel(const float *__restrict__ src, int n_types, int kp, float *__restrict__ dst)
-{
-    for (int i = threadIdx.x; i < kp * kp; i += blockDim.x) {
-        const int a = i / kp, c = i - a * kp;
-        dst[i] = (a < n_types && c < n_types) ? src[a * n_types + c] : 0.f;
     }
 }
 
@@ -467,21 +463,17 @@ extern "C" __attribute__((visibility("default"))) int fdb_objective_terms(const 
     if (n_rows == 0) return FDB_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int kp = fdb_padded_types(n_types);
-    // stage the padded Gram through a small async allocation (stream ordered)
-    float *gram_dev = nullptr, *gram_pad = nullptr;
-    FDB_CUDA(cudaMallocAsync((void **)&gram_dev, (size_t)n_types * n_types * 4 + (size_t)kp * kp * 4, st));
-    gram_pad = gram_dev + (size_t)n_types * n_types;
-    FDB_CUDA(cudaMemcpyAsync(gram_dev, host_gram, (size_t)n_types * n_types * 4, cudaMemcpyHostToDevice, st));
-    pad_gram_kernel<<<1, 256, 0, st>>>(gram_dev, n_types, kp, gram_pad);
+    GramFull gram;
+    for (int i = 0; i < kp * kp; ++i) gram.g[i] = 0.f;
+    for (int a = 0; a < n_types; ++a)
+        for (int c = 0; c < n_types; ++c) gram.g[a * kp + c] = host_gram[a * n_types + c];
     const int grid = (int)std::min<int64_t>(ceil_div(n_rows, 8), (int64_t)kNumSM * 8);
     const size_t smem = (size_t)kp * kp * 4;
     if (kp <= 32)
-        objective_kernel<1><<<grid, 256, smem, st>>>(beta, h, ysq, gram_pad, indptr, indices, n_rows, kp, out);
+        objective_kernel<1><<<grid, 256, smem, st>>>(beta, h, ysq, gram, indptr, indices, n_rows, kp, out);
     else
-        objective_kernel<2><<<grid, 256, smem, st>>>(beta, h, ysq, gram_pad, indptr, indices, n_rows, kp, out);
-    count_launches(1);
+        objective_kernel<2><<<grid, 256, smem, st>>>(beta, h, ysq, gram, indptr, indices, n_rows, kp, out);
     FDB_LAUNCH_CHECK("objective_kernel");
-    FDB_CUDA(cudaFreeAsync(gram_dev, st));
     return FDB_OK;
 }
 

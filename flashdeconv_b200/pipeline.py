@@ -24,7 +24,11 @@ GRAPH_MODES = {"knn": 0, "radius": 1, "grid": 2}
 
 
 def _ptr(t):
-    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+    if t is None:
+        return C.c_void_p(0)
+    if not t.is_contiguous():
+        raise ValueError("libfdb200 takes dense row-major buffers; got a non-contiguous tensor")
+    return C.c_void_p(t.data_ptr())
 
 
 def _stream(torch):

@@ -144,7 +144,8 @@ def compute_objective(beta: np.ndarray, H: np.ndarray, XtX: np.ndarray, YtY: flo
     A.sort_indices()
     if A.nnz and not np.allclose(A.data, 1.0):
         raise NotImplementedError("compute_objective on the device expects the Laplacian of a binary adjacency")
-    pad = lambda M: torch.from_numpy(np.pad(np.asarray(M, dtype=np.float32), ((0, 0), (0, kp - K)))).cuda()
+    pad = lambda M: torch.from_numpy(np.ascontiguousarray(
+        np.pad(np.asarray(M, dtype=np.float32), ((0, 0), (0, kp - K))))).cuda()
     b, h = pad(beta), pad(np.asarray(H).T)
     ysq = torch.zeros(n, dtype=torch.float32, device="cuda")
     ip = torch.from_numpy(A.indptr.astype(np.int32)).cuda()
