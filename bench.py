@@ -194,6 +194,7 @@ def main():
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
         barrier()
+        torch.cuda.profiler.start()          # no-op unless run under `ncu --profile-from-start off`
         start.record()
         for _ in range(args.steps):
             ev = {}
@@ -201,6 +202,7 @@ def main():
             stage_events = ev
         end.record()
         barrier()
+        torch.cuda.profiler.stop()
     elapsed_ms = start.elapsed_time(end)
     launches = (lib.fdb_launch_count() - launches0) // args.steps
     for name, (a, b) in stage_events.items():

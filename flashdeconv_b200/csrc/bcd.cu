@@ -16,10 +16,10 @@
 //     its beta row and its neighbours' beta rows -- and leave c = H + lam * nsum and beta_old in
 //     shared memory.
 //   phase B (thread per spot): the K-step coordinate descent is strictly sequential per spot, so
-//     each lane runs one spot with the maintained product r[Kp] in registers; the Gram matrix is
-//     a by-value kernel parameter, i.e. every FFMA takes its G operand straight from the constant
-//     bank.  Rank-1 updates are skipped warp-uniformly when no lane moved (most coordinates sit
-//     at the non-negativity bound).
+//     each lane runs one spot with its beta row in registers and evaluates the partial residual
+//     in the direct form part_k = c_k - sum_{j!=k} G_kj b_j (K^2 FMAs per spot, the dense minimum;
+//     the reference's maintained-residual form costs 1.5-2 K^2 under SIMT).  The Gram matrix is a
+//     by-value kernel parameter: every FFMA takes its G operand from the constant bank.
 //   phase C (coalesced): the warp streams its 32 new rows back out.
 //   Convergence statistics: redux.sync max per warp, one atomicMax per CTA, last CTA finalises.
 #include <algorithm>
@@ -44,12 +44,22 @@ static_assert(sizeof(SolveState) == 64, "state block is 64 bytes");
 
 template <int KP>
 struct GramArg {
-    float g[KP * KP];               // g[k * KP + a] = G[a][k] (symmetric), zero padded
+    float g[KP * KP];               // g[k*KP+j] = -G[k][j] for j != k, 0 on the diagonal; zero padded
+    float diag[KP];                 // G[k][k]
 };
 
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 __device__ __forceinline__ void add4(float4 &a, const float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+// packed fp32x2 FMA (sm_100+): d = a * b + d on both halves, one issue slot
+__device__ __forceinline__ void ffma2(float2 &d, const float2 a, const float2 b)
+{
+    unsigned long long ua = *reinterpret_cast<const unsigned long long *>(&a);
+    unsigned long long ub = *reinterpret_cast<const unsigned long long *>(&b);
+    unsigned long long ud = *reinterpret_cast<unsigned long long *>(&d);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(ud) : "l"(ua), "l"(ub));
+    d = *reinterpret_cast<float2 *>(&ud);
+}
 __device__ __forceinline__ float elem(const float4 &v, int j) { return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w; }
 __device__ __forceinline__ void set_elem(float4 &v, int j, float x)
 {
@@ -72,13 +82,14 @@ __device__ __forceinline__ void finalize_state(SolveState *st, float tol)
 
 constexpr int kSweepThreads = 128;
 constexpr int kNbrUnroll = 8;
+constexpr int kIdxCap = 512;        // neighbour indices staged in shared memory per warp (32 spots)
 
 template <int KP>
 __global__ void __launch_bounds__(kSweepThreads)
 bcd_sweep_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP> G,
                  const float *__restrict__ beta_in, float *__restrict__ beta_out,
                  const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
-                 int n_rows, float lam, float rho, float tol, int finalize, SolveState *state)
+                 int n_rows, int n_types, float lam, float rho, float tol, int finalize, SolveState *state)
 {
     if (*reinterpret_cast<volatile int *>(&state->converged)) return;
 
@@ -89,35 +100,49 @@ bcd_sweep_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP
     extern __shared__ __align__(16) float sweep_smem[];
     float *c_tile = sweep_smem;
     float *b_tile = sweep_smem + kSweepThreads * S;
-    int *deg_tile = reinterpret_cast<int *>(sweep_smem + 2 * kSweepThreads * S);
+    int *idx_tile = reinterpret_cast<int *>(sweep_smem + 2 * kSweepThreads * S);
     __shared__ unsigned red[2][kSweepThreads / 32];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wbase = blockIdx.x * kSweepThreads + warp * 32;
     float *cw = c_tile + warp * 32 * S;
     float *bw = b_tile + warp * 32 * S;
-    int *dw = deg_tile + warp * 32;
+    int *iw = idx_tile + warp * kIdxCap;
 
     // ---------------- phase A: stream rows, build c = H + lam * sum_j beta_old[j]
+    // A0: the warp's 33 row pointers (lane = row) and its contiguous slice of neighbour indices -> smem,
+    //     so the row gathers below depend on shared memory only (one global round trip, not three).
+    const int my_row = wbase + lane;
+    int my_s = 0, my_e = 0;
+    if (my_row < n_rows) { my_s = __ldg(indptr + my_row); my_e = __ldg(indptr + my_row + 1); }
+    const int my_deg = my_e - my_s;
+    const int ibase = __shfl_sync(kFull, my_s, 0);
+    int icnt = my_e - ibase;                             // running end of the warp's slice
+    icnt = __reduce_max_sync(kFull, icnt);
+    const bool staged = icnt <= kIdxCap;
+    if (staged)
+        for (int t = lane; t < icnt; t += 32) iw[t] = __ldg(indices + ibase + t);
+    __syncwarp();
     {
         const int slot = lane / Q, q = lane - slot * Q;
-#pragma unroll 1
+#pragma unroll 2
         for (int it = 0; it < ITERS; ++it) {
             const int lr = it * SLOTS + slot;
+            const int src = lr < 32 ? lr : 31;
+            const int rs = __shfl_sync(kFull, my_s, src) - ibase;
+            const int deg = __shfl_sync(kFull, my_deg, src);
             const int p = wbase + lr;
             if (slot < SLOTS && lr < 32) {
                 float4 own = make_float4(0.f, 0.f, 0.f, 0.f), cc = own;
-                int deg = 0;
                 if (p < n_rows) {
-                    const int s = __ldg(indptr + p), e = __ldg(indptr + p + 1);
-                    deg = e - s;
                     own = ld4(beta_in + (size_t)p * KP + 4 * q);
                     cc = __ldcs(reinterpret_cast<const float4 *>(h + (size_t)p * KP + 4 * q));
                     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int j0 = s; j0 < e; j0 += kNbrUnroll) {
+                    for (int j0 = 0; j0 < deg; j0 += kNbrUnroll) {
                         int nb[kNbrUnroll];
 #pragma unroll
-                        for (int u = 0; u < kNbrUnroll; ++u) nb[u] = j0 + u < e ? __ldg(indices + j0 + u) : -1;
+                        for (int u = 0; u < kNbrUnroll; ++u)
+                            nb[u] = j0 + u < deg ? (staged ? iw[rs + j0 + u] : __ldg(indices + ibase + rs + j0 + u)) : -1;
                         float4 v[kNbrUnroll];
 #pragma unroll
                         for (int u = 0; u < kNbrUnroll; ++u)
@@ -132,61 +157,55 @@ bcd_sweep_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP
                 }
                 st4(cw + lr * S + 4 * q, cc);
                 st4(bw + lr * S + 4 * q, own);
-                if (q == 0) dw[lr] = deg;
             }
         }
     }
     __syncwarp();
 
-    // ---------------- phase B: one spot per lane, cyclic coordinate descent
+    // ---------------- phase B: one spot per lane, cyclic coordinate descent in the direct form
+    //   part_k = c_k - sum_{j != k} G_kj b_j   (b_j already updated for j < k)
+    // G.g holds the NEGATED Gram with a zero diagonal, so step k is Kp/2 packed FFMA2 (fma.rn.f32x2, two
+    // fp32 FMAs per issue slot on sm_100) whose G operand pair comes from the constant bank via LDCU.128.
     float dmax = 0.f, amax = 0.f;
     {
-        const float lam_deg = lam * (float)dw[lane];
-        float r[KP];
-#pragma unroll
-        for (int a = 0; a < KP; ++a) r[a] = 0.f;
+        const float lam_deg = lam * (float)my_deg;
+        float2 b2[KP / 2];
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
             const float4 b4 = ld4(bw + lane * S + 4 * q);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = 4 * q + j;
-                const float bk = elem(b4, j);
-                if (__any_sync(kFull, bk != 0.f)) {
-#pragma unroll
-                    for (int a = 0; a < KP; ++a) r[a] = fmaf(bk, G.g[k * KP + a], r[a]);
-                }
-            }
+            b2[2 * q] = make_float2(b4.x, b4.y);
+            b2[2 * q + 1] = make_float2(b4.z, b4.w);
         }
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
-            const float4 b4 = ld4(bw + lane * S + 4 * q);
             const float4 c4 = ld4(cw + lane * S + 4 * q);
-            float4 n4;
+            float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int k = 4 * q + j;
-                const float old = elem(b4, j);
-                const float gkk = G.g[k * KP + k];
-                const float part = elem(c4, j) - r[k] + gkk * old;
-                const float den = gkk + lam_deg;
+                if (k >= KP - 3 && k >= n_types) continue;          // padding columns stay zero (warp-uniform)
+                float2 a0 = make_float2(elem(c4, j), 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int jj = 0; jj < KP / 2; ++jj) {
+                    const float2 g = make_float2(G.g[k * KP + 2 * jj], G.g[k * KP + 2 * jj + 1]);
+                    if (jj & 1) ffma2(a1, g, b2[jj]); else ffma2(a0, g, b2[jj]);
+                }
+                const float part = (a0.x + a0.y) + (a1.x + a1.y);
+                const float old = (k & 1) ? b2[k / 2].y : b2[k / 2].x;
+                const float den = G.diag[k] + lam_deg;
                 float nv = 0.f;
                 if (den > 1e-10f) {
                     const float sh = part > rho ? part - rho : (part < -rho ? part + rho : 0.f);
-                    nv = fmaxf(0.f, sh / den);
+                    nv = fmaxf(0.f, __fdividef(sh, den));
                 }
-                const float delta = nv - old;
-                if (__any_sync(kFull, delta != 0.f)) {
-#pragma unroll
-                    for (int a = 0; a < KP; ++a) r[a] = fmaf(delta, G.g[k * KP + a], r[a]);
-                }
-                dmax = fmaxf(dmax, fabsf(delta));
+                dmax = fmaxf(dmax, fabsf(nv - old));
                 amax = fmaxf(amax, fabsf(old));
+                if (k & 1) b2[k / 2].y = nv; else b2[k / 2].x = nv;
                 set_elem(n4, j, nv);
             }
             st4(bw + lane * S + 4 * q, n4);
         }
-        if (wbase + lane >= n_rows) { dmax = 0.f; amax = 0.f; }
+        if (my_row >= n_rows) { dmax = 0.f; amax = 0.f; }
     }
     __syncwarp();
 
@@ -245,18 +264,19 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
 {
     GramArg<KP> G;
     for (int i = 0; i < KP * KP; ++i) G.g[i] = 0.f;
+    for (int k = 0; k < KP; ++k) G.diag[k] = k < n_types ? host_gram[k * n_types + k] : 0.f;
     for (int k = 0; k < n_types; ++k)
-        for (int a = 0; a < n_types; ++a) G.g[k * KP + a] = host_gram[a * n_types + k];
+        for (int a = 0; a < n_types; ++a) G.g[k * KP + a] = (a == k) ? 0.f : -host_gram[k * n_types + a];
     const int grid = (int)ceil_div(n_rows, kSweepThreads);
     constexpr int S = ((KP / 4) % 2 == 1) ? KP : KP + 4;
-    constexpr size_t smem = (size_t)kSweepThreads * (2 * S + 1) * 4;
+    constexpr size_t smem = (size_t)kSweepThreads * 2 * S * 4 + (size_t)(kSweepThreads / 32) * kIdxCap * 4;
     static bool configured = false;              // per instantiation
     if (!configured) {
         FDB_CUDA(cudaFuncSetAttribute(bcd_sweep_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
     bcd_sweep_kernel<KP><<<grid, kSweepThreads, smem, st>>>(h, G, beta_in, beta_out, indptr, indices, (int)n_rows,
-                                                         lam, rho, tol, finalize, state);
+                                                         n_types, lam, rho, tol, finalize, state);
     FDB_LAUNCH_CHECK("bcd_sweep_kernel");
     return FDB_OK;
 }
