@@ -23,6 +23,7 @@
 //   phase C (coalesced): the warp streams its 32 new rows back out.
 //   Convergence statistics: redux.sync max per warp, one atomicMax per CTA, last CTA finalises.
 #include <algorithm>
+#include <stdlib.h>
 #include "fdb_common.cuh"
 
 extern "C" __attribute__((visibility("default"))) int fdb_bcd_init(float *beta, int64_t n_rows, int32_t n_types, void *state, void *stream);
@@ -238,6 +239,223 @@ bcd_sweep_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP
     }
 }
 
+// ------------------------------------------------------------------------------------
+// Sweep kernel, warp-specialised persistent form (production).
+//
+// The gather of neighbour rows is latency-bound and the coordinate descent is issue-bound; run as
+// consecutive phases of one warp they serialise (CTAs of a wave even fall into lock-step).  Here a
+// CTA is 4 producer warps + 4 consumer warps; producer i streams rows for 32-spot tiles into one of
+// two shared-memory stages and hands them to consumer i through mbarriers, so the SM always has row
+// loads in flight while the FMA pipe runs the descent of earlier tiles.  Tiles are strided over all
+// producer/consumer pairs of a persistent grid (a few CTAs per SM).
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+
+constexpr int kWsPairs = 4;                       // producer/consumer pairs per CTA
+constexpr int kWsThreads = kWsPairs * 64;
+constexpr int kWsIdxCap = 384;                    // staged neighbour indices per tile
+
+template <int KP>
+struct WsLayout {
+    static constexpr int Q = KP / 4;
+    static constexpr bool SWZ = (Q % 8 == 0);                             // XOR swizzle instead of padding
+    static constexpr int S = SWZ ? KP : ((Q % 2 == 1) ? KP : KP + 4);     // floats per staged row
+    static constexpr int kStageFloats = 2 * 32 * S + 32;                  // c tile, b tile, degrees
+    static constexpr int kPairFloats = 2 * kStageFloats + kWsIdxCap;
+    static constexpr size_t kSmemBytes = (size_t)kWsPairs * kPairFloats * 4 + 64;
+    __device__ static __forceinline__ int at(int row, int q)              // float offset of chunk q of a row
+    {
+        return SWZ ? row * S + 4 * (q ^ (row & 7)) : row * S + 4 * q;
+    }
+};
+
+template <int KP>
+__global__ void __launch_bounds__(kWsThreads)
+bcd_sweep_ws_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP> G,
+                    const float *__restrict__ beta_in, float *__restrict__ beta_out,
+                    const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                    int n_rows, int n_types, float lam, float rho, float tol, int finalize, SolveState *state)
+{
+    if (*reinterpret_cast<volatile int *>(&state->converged)) return;
+    using L = WsLayout<KP>;
+    constexpr int Q = L::Q, SLOTS = 32 / Q, ITERS = (32 + SLOTS - 1) / SLOTS;
+
+    extern __shared__ __align__(16) float ws_smem[];
+    __shared__ __align__(8) uint64_t bars[kWsPairs][2][2];               // [pair][stage][0 = full, 1 = empty]
+    __shared__ unsigned red[2][kWsPairs];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool producer = warp < kWsPairs;
+    const int pair = producer ? warp : warp - kWsPairs;
+    float *pair_smem = ws_smem + (size_t)pair * L::kPairFloats;
+    int *iw = reinterpret_cast<int *>(pair_smem + 2 * L::kStageFloats);
+
+    if (threadIdx.x < kWsPairs * 4) mbar_init(&bars[0][0][0] + threadIdx.x, 1);
+    __syncthreads();
+
+    const int n_tiles = (n_rows + 31) / 32;
+    const int pair_global = blockIdx.x * kWsPairs + pair;
+    const int pair_stride = gridDim.x * kWsPairs;
+    float dmax = 0.f, amax = 0.f;
+
+    if (producer) {
+        // ================= producer: stream rows, leave c = H + lam * sum_j beta_old[j] and beta_old in a stage
+        const int slot = lane / Q, q = lane - slot * Q;
+        int n = 0;
+        for (int tile = pair_global; tile < n_tiles; tile += pair_stride, ++n) {
+            const int st = n & 1;
+            float *cw = pair_smem + st * L::kStageFloats;
+            float *bw = cw + 32 * L::S;
+            int *dw = reinterpret_cast<int *>(bw + 32 * L::S);
+            const int wbase = tile * 32;
+            const int my_row = wbase + lane;
+            int my_s = 0, my_e = 0;
+            if (my_row < n_rows) { my_s = __ldg(indptr + my_row); my_e = __ldg(indptr + my_row + 1); }
+            const int my_deg = my_e - my_s;
+            const int ibase = __shfl_sync(kFull, my_s, 0);
+            const int icnt = __reduce_max_sync(kFull, my_e - ibase);
+            const bool staged = icnt <= kWsIdxCap;
+            // the stage (and the index buffer, which the previous tile's gathers no longer need) must be free
+            mbar_wait(&bars[pair][st][1], ((n >> 1) & 1) ^ 1);
+            if (staged)
+                for (int t = lane; t < icnt; t += 32) iw[t] = __ldg(indices + ibase + t);
+            dw[lane] = my_deg;
+            __syncwarp();
+#pragma unroll 2
+            for (int it = 0; it < ITERS; ++it) {
+                const int lr = it * SLOTS + slot;
+                const int src = lr < 32 ? lr : 31;
+                const int rs = __shfl_sync(kFull, my_s, src) - ibase;
+                const int deg = __shfl_sync(kFull, my_deg, src);
+                const bool active = slot < SLOTS && lr < 32;
+                const int p = wbase + lr;
+                const bool live = active && p < n_rows;
+                const int trip = __reduce_max_sync(kFull, live ? deg : 0);
+                float4 own = make_float4(0.f, 0.f, 0.f, 0.f), cc = own, acc = own;
+                const int pc = live ? p : 0;                                   // clamp: loads stay in bounds
+                if (live) {
+                    own = ld4(beta_in + (size_t)pc * KP + 4 * q);
+                    cc = __ldcs(reinterpret_cast<const float4 *>(h + (size_t)pc * KP + 4 * q));
+                }
+#pragma unroll 4
+                for (int u = 0; u < trip; ++u) {
+                    // absent neighbours read the spot's own (cache-hot) row with weight 0: no branches
+                    const bool has = live && u < deg;
+                    int nb = pc;
+                    if (has) nb = staged ? iw[rs + u] : __ldg(indices + ibase + rs + u);
+                    const float4 v = ld4(beta_in + (size_t)nb * KP + 4 * q);
+                    const float m = has ? 1.f : 0.f;
+                    acc.x = fmaf(v.x, m, acc.x); acc.y = fmaf(v.y, m, acc.y);
+                    acc.z = fmaf(v.z, m, acc.z); acc.w = fmaf(v.w, m, acc.w);
+                }
+                if (active) {
+                    cc.x = fmaf(lam, acc.x, cc.x); cc.y = fmaf(lam, acc.y, cc.y);
+                    cc.z = fmaf(lam, acc.z, cc.z); cc.w = fmaf(lam, acc.w, cc.w);
+                    st4(cw + L::at(lr, q), cc);
+                    st4(bw + L::at(lr, q), own);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[pair][st][0]);
+        }
+    } else {
+        // ================= consumer: one spot per lane, cyclic coordinate descent (direct form, FFMA2)
+        int n = 0;
+        for (int tile = pair_global; tile < n_tiles; tile += pair_stride, ++n) {
+            const int st = n & 1;
+            float *cw = pair_smem + st * L::kStageFloats;
+            float *bw = cw + 32 * L::S;
+            const int *dw = reinterpret_cast<const int *>(bw + 32 * L::S);
+            const int wbase = tile * 32;
+            mbar_wait(&bars[pair][st][0], (n >> 1) & 1);
+            const float lam_deg = lam * (float)dw[lane];
+            float2 b2[KP / 2];
+#pragma unroll
+            for (int qq = 0; qq < Q; ++qq) {
+                const float4 b4 = ld4(bw + L::at(lane, qq));
+                b2[2 * qq] = make_float2(b4.x, b4.y);
+                b2[2 * qq + 1] = make_float2(b4.z, b4.w);
+            }
+            float tdmax = 0.f, tamax = 0.f;
+#pragma unroll
+            for (int qq = 0; qq < Q; ++qq) {
+                const float4 c4 = ld4(cw + L::at(lane, qq));
+                float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int k = 4 * qq + j;
+                    if (k >= KP - 3 && k >= n_types) continue;              // padding columns stay zero (uniform)
+                    float2 a0 = make_float2(elem(c4, j), 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int jj = 0; jj < KP / 2; ++jj) {
+                        const float2 g = make_float2(G.g[k * KP + 2 * jj], G.g[k * KP + 2 * jj + 1]);
+                        if (jj & 1) ffma2(a1, g, b2[jj]); else ffma2(a0, g, b2[jj]);
+                    }
+                    const float part = (a0.x + a0.y) + (a1.x + a1.y);
+                    const float old = (k & 1) ? b2[k / 2].y : b2[k / 2].x;
+                    const float den = G.diag[k] + lam_deg;
+                    float nv = 0.f;
+                    if (den > 1e-10f) {
+                        const float sh = part > rho ? part - rho : (part < -rho ? part + rho : 0.f);
+                        nv = fmaxf(0.f, __fdividef(sh, den));
+                    }
+                    tdmax = fmaxf(tdmax, fabsf(nv - old));
+                    tamax = fmaxf(tamax, fabsf(old));
+                    if (k & 1) b2[k / 2].y = nv; else b2[k / 2].x = nv;
+                    set_elem(n4, j, nv);
+                }
+                st4(bw + L::at(lane, qq), n4);
+            }
+            if (wbase + lane < n_rows) { dmax = fmaxf(dmax, tdmax); amax = fmaxf(amax, tamax); }
+            __syncwarp();
+            // stream the 32 new rows out (coalesced), then release the stage
+#pragma unroll
+            for (int i = 0; i < Q; ++i) {
+                const int idx = lane + 32 * i;
+                const int lr = idx / Q, qq = idx - lr * Q;
+                if (wbase + lr < n_rows) st4(beta_out + (size_t)(wbase + lr) * KP + 4 * qq, ld4(bw + L::at(lr, qq)));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[pair][st][1]);
+        }
+        const unsigned wd = __reduce_max_sync(kFull, __float_as_uint(dmax));
+        const unsigned wa = __reduce_max_sync(kFull, __float_as_uint(amax));
+        if (lane == 0) { red[0][pair] = wd; red[1][pair] = wa; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned bd = 0u, ba = 0u;
+#pragma unroll
+        for (int w = 0; w < kWsPairs; ++w) { bd = max(bd, red[0][w]); ba = max(ba, red[1][w]); }
+        if (bd > *reinterpret_cast<volatile unsigned *>(&state->max_diff_bits)) atomicMax(&state->max_diff_bits, bd);
+        if (ba > *reinterpret_cast<volatile unsigned *>(&state->max_abs_bits)) atomicMax(&state->max_abs_bits, ba);
+        if (finalize) {
+            __threadfence();
+            if (atomicAdd(&state->arrived, 1u) == gridDim.x - 1) {
+                __threadfence();
+                finalize_state(state, tol);
+            }
+        }
+    }
+}
+
 __global__ void bcd_finalize_kernel(SolveState *state, float tol)
 {
     if (state->converged) return;
@@ -267,6 +485,25 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
     for (int k = 0; k < KP; ++k) G.diag[k] = k < n_types ? host_gram[k * n_types + k] : 0.f;
     for (int k = 0; k < n_types; ++k)
         for (int a = 0; a < n_types; ++a) G.g[k * KP + a] = (a == k) ? 0.f : -host_gram[k * n_types + a];
+    static const bool use_v2 = getenv("FDB_SWEEP_V2") != nullptr;
+    if (!use_v2) {
+        using L = WsLayout<KP>;
+        static int ctas_per_sm = 0;
+        if (!ctas_per_sm) {
+            FDB_CUDA(cudaFuncSetAttribute(bcd_sweep_ws_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)L::kSmemBytes));
+            FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, bcd_sweep_ws_kernel<KP>, kWsThreads,
+                                                                   L::kSmemBytes));
+            if (ctas_per_sm < 1) ctas_per_sm = 1;
+        }
+        const int64_t tiles = ceil_div(n_rows, 32);
+        const int grid = (int)std::min<int64_t>(ceil_div(tiles, kWsPairs), (int64_t)kNumSM * ctas_per_sm);
+        bcd_sweep_ws_kernel<KP><<<grid, kWsThreads, L::kSmemBytes, st>>>(h, G, beta_in, beta_out, indptr, indices,
+                                                                         (int)n_rows, n_types, lam, rho, tol,
+                                                                         finalize, state);
+        FDB_LAUNCH_CHECK("bcd_sweep_ws_kernel");
+        return FDB_OK;
+    }
     const int grid = (int)ceil_div(n_rows, kSweepThreads);
     constexpr int S = ((KP / 4) % 2 == 1) ? KP : KP + 4;
     constexpr size_t smem = (size_t)kSweepThreads * 2 * S * 4 + (size_t)(kSweepThreads / 32) * kIdxCap * 4;

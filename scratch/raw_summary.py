@@ -1,0 +1,24 @@
+"""Key metrics per kernel from `ncu --page raw --csv`."""
+import csv, sys
+rows = list(csv.reader(open(sys.argv[1])))
+hdr, units = rows[0], rows[1]
+idx = {h: i for i, h in enumerate(hdr)}
+want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'launch__registers_per_thread',
+        'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_warps',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'l1tex__throughput.avg.pct_of_peak_sustained_active',
+        'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'lts__t_sector_hit_rate.pct',
+        'l1tex__t_sector_hit_rate.pct', 'launch__grid_size', 'launch__block_size',
+        'smsp__thread_inst_executed_per_inst_executed.ratio', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
+        'smsp__inst_executed_pipe_lsu.sum', 'l1tex__data_pipe_lsu_wavefronts.sum', 'smsp__cycles_active.avg',
+        'launch__shared_mem_per_block_dynamic', 'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_uniform.sum']
+seen = set()
+for r in rows[2:]:
+    name = r[idx['Kernel Name']][:70]
+    if name in seen: continue
+    seen.add(name)
+    print('-----', name)
+    for w in want:
+        if w in idx: print(f"  {w:75s} {r[idx[w]]:>18s} {units[idx[w]]}")

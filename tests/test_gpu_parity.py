@@ -99,6 +99,54 @@ def test_sketch_ragged_rows_vs_oracle(fo, n, G, d, density):
     assert rel(out.cpu().numpy(), want) <= Y_REL_TOL
 
 
+@pytest.mark.parametrize("n,G,K,d,density,frac_sel,v1", [
+    (300, 3000, 7, 512, 0.3, 1.0, False),      # ~900 selected per row: compaction list overflows -> re-stream path
+    (500, 2500, 40, 256, 0.1, 0.5, False),     # K > 32: two accumulators per lane
+    (64, 1000, 64, 64, 0.2, 0.3, False),
+    (2, 70000, 5, 128, 0.01, 0.2, False),      # gene axis too wide for the shared-memory table -> v1 kernel
+    (400, 2000, 12, 128, 0.1, 0.4, True),      # v1 kernel forced
+])
+def test_fused_sketch_ragged_vs_oracle(fo, monkeypatch, n, G, K, d, density, frac_sel, v1):
+    import torch
+    from flashdeconv_b200 import pipeline as pl
+    if v1:
+        monkeypatch.setenv("FDB_SKETCH_V1", "1")
+    rng = np.random.default_rng(G + K)
+    Y = sparse.random(n, G, density=density, format="csr", random_state=np.random.RandomState(K),
+                      data_rvs=lambda s: rng.integers(1, 30, s).astype(np.float64))
+    Y = sparse.vstack([Y[:1], sparse.csr_matrix((1, G)), Y[2:]]).tocsr()              # one empty row
+    X = rng.random((K, G)) + 0.05
+    gene_idx = np.sort(rng.choice(G, size=max(int(G * frac_sel), 1), replace=False))
+    lev = rng.random(gene_idx.size)
+    tables = pl.build_tables(X, gene_idx, lev, d, 5, G)
+    path = pl.DevicePath(pl.csr_to_device(Y), torch.zeros((n, 2), dtype=torch.float64, device="cuda"), tables, K)
+    path.stage_sketch()
+    torch.cuda.synchronize()
+    Ys = fo.sketch_full_csr(Y, gene_idx, tables.bucket, tables.weight, d)
+    assert rel(path.h.cpu().numpy()[:, :K], Ys @ tables.X_sketch.T) <= Y_REL_TOL
+    assert rel(path.ysq.cpu().numpy(), (Ys ** 2).sum(1)) <= Y_REL_TOL
+    assert np.all(path.h.cpu().numpy()[:, K:] == 0)
+
+
+def test_sweep_kernel_variants_agree(monkeypatch):
+    """warp-specialised persistent sweep (default) == one-CTA-per-tile sweep (FDB_SWEEP_V2), bit for bit"""
+    import subprocess, sys, os
+    from conftest import ROOT
+    code = ("import numpy as np, hashlib, sys; sys.path.insert(0, %r);"
+            "from flashdeconv_b200.solver import bcd_solve; from flashdeconv_b200.graph import build_knn_graph;"
+            "rng = np.random.default_rng(7); n, K, d = 5000, 30, 64;"
+            "Xs = rng.standard_normal((K, d)) + 0.3; Ys = (rng.random((n, K)) * (rng.random((n, K)) < 0.3)) @ Xs;"
+            "A = build_knn_graph(rng.random((n, 2)), k=6);"
+            "b, info = bcd_solve(Ys, Xs, A, lambda_=1.0, rho=0.01, max_iter=20, tol=1e-12);"
+            "print(hashlib.sha256(b.tobytes()).hexdigest(), info['n_iterations'])" % ROOT)
+    outs = []
+    for env_extra in ({}, {"FDB_SWEEP_V2": "1"}):
+        env = dict(os.environ, **env_extra)
+        outs.append(subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300))
+    assert outs[0].returncode == 0 and outs[1].returncode == 0, outs[0].stderr + outs[1].stderr
+    assert outs[0].stdout.strip() == outs[1].stdout.strip() and outs[0].stdout.split()[1] == "20"
+
+
 def test_projection_is_linear():
     """reference tests/test_sketching.py:95-110"""
     from flashdeconv_b200.sketching import build_countsketch_matrix, project_to_sketch
