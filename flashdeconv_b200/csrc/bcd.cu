@@ -81,12 +81,30 @@ __device__ __forceinline__ void finalize_state(SolveState *st, float tol)
     st->arrived = 0u;
 }
 
-constexpr int kSweepThreads = 128;
-constexpr int kNbrUnroll = 8;
-constexpr int kIdxCap = 512;        // neighbour indices staged in shared memory per warp (32 spots)
+constexpr int kIdxCap = 256;        // neighbour indices staged in shared memory per warp (32 spots)
 
 template <int KP>
-__global__ void __launch_bounds__(kSweepThreads)
+struct TileLayout {
+    static constexpr int Q = KP / 4;                                      // float4 chunks per row
+    static constexpr bool SWZ = (Q % 8 == 0);                             // XOR swizzle instead of padding
+    static constexpr int S = SWZ ? KP : ((Q % 2 == 1) ? KP : KP + 4);     // floats per staged row
+    __device__ static __forceinline__ int at(int row, int q)              // float offset of chunk q of a row
+    {
+        return SWZ ? row * S + 4 * (q ^ (row & 7)) : row * S + 4 * q;
+    }
+};
+
+// Sweep kernel, tile-cached form (production).  One CTA = NW warps = TILE = 32*NW consecutive spots
+// (tile order => a compact patch of the tissue).
+//   step 1  the CTA streams its TILE beta_old rows and H rows into shared memory with fully
+//           independent coalesced 128-bit loads (one global round trip, 2*Kp/4 loads in flight per thread);
+//   step 2  neighbour sums: groups of Kp/4 lanes walk a spot's neighbour list; a neighbour inside the
+//           CTA's patch (75-85 % of them) is read from the shared tile, the rest from global/L2;
+//           c = H + lam * sum is left in shared memory;
+//   step 3  one spot per lane: cyclic coordinate descent in the direct form on packed FFMA2;
+//   step 4  the warp streams its 32 new rows back out.
+template <int KP, int NW>
+__global__ void __launch_bounds__(NW * 32)
 bcd_sweep_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP> G,
                  const float *__restrict__ beta_in, float *__restrict__ beta_out,
                  const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
@@ -94,92 +112,100 @@ bcd_sweep_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP
 {
     if (*reinterpret_cast<volatile int *>(&state->converged)) return;
 
-    constexpr int Q = KP / 4;                           // float4 chunks per row
-    constexpr int S = (Q % 2 == 1) ? KP : KP + 4;       // smem row stride: odd chunk count => conflict-free 128-bit rows
-    constexpr int SLOTS = 32 / Q;                       // rows streamed per warp instruction
+    using L = TileLayout<KP>;
+    constexpr int Q = L::Q, S = L::S, TILE = NW * 32;
+    constexpr int SLOTS = 32 / Q;                       // rows walked per warp instruction
     constexpr int ITERS = (32 + SLOTS - 1) / SLOTS;
     extern __shared__ __align__(16) float sweep_smem[];
     float *c_tile = sweep_smem;
-    float *b_tile = sweep_smem + kSweepThreads * S;
-    int *idx_tile = reinterpret_cast<int *>(sweep_smem + 2 * kSweepThreads * S);
-    __shared__ unsigned red[2][kSweepThreads / 32];
+    float *b_tile = sweep_smem + TILE * S;
+    int *idx_tile = reinterpret_cast<int *>(sweep_smem + 2 * TILE * S);
+    __shared__ unsigned red[2][NW];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int wbase = blockIdx.x * kSweepThreads + warp * 32;
-    float *cw = c_tile + warp * 32 * S;
-    float *bw = b_tile + warp * 32 * S;
+    const int tile_base = blockIdx.x * TILE;
+    const int wrow = warp * 32;                          // first tile row of this warp
     int *iw = idx_tile + warp * kIdxCap;
 
-    // ---------------- phase A: stream rows, build c = H + lam * sum_j beta_old[j]
-    // A0: the warp's 33 row pointers (lane = row) and its contiguous slice of neighbour indices -> smem,
-    //     so the row gathers below depend on shared memory only (one global round trip, not three).
-    const int my_row = wbase + lane;
+    // ---------------- step 0/1: row pointers, then the tile's rows and the warp's index slice
+    const int my_row = tile_base + wrow + lane;
     int my_s = 0, my_e = 0;
     if (my_row < n_rows) { my_s = __ldg(indptr + my_row); my_e = __ldg(indptr + my_row + 1); }
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        const int idx = threadIdx.x + i * TILE;
+        const int row = idx / Q, q = idx - row * Q;
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f), hh = bb;
+        if (tile_base + row < n_rows) {
+            bb = ld4(beta_in + (size_t)(tile_base + row) * KP + 4 * q);
+            hh = __ldcs(reinterpret_cast<const float4 *>(h + (size_t)(tile_base + row) * KP + 4 * q));
+        }
+        st4(b_tile + L::at(row, q), bb);
+        st4(c_tile + L::at(row, q), hh);
+    }
     const int my_deg = my_e - my_s;
     const int ibase = __shfl_sync(kFull, my_s, 0);
-    int icnt = my_e - ibase;                             // running end of the warp's slice
-    icnt = __reduce_max_sync(kFull, icnt);
+    const int icnt = __reduce_max_sync(kFull, my_e - ibase);
     const bool staged = icnt <= kIdxCap;
     if (staged)
         for (int t = lane; t < icnt; t += 32) iw[t] = __ldg(indices + ibase + t);
-    __syncwarp();
+    __syncthreads();
+
+    // ---------------- step 2: c += lam * sum_j beta_old[j]
     {
         const int slot = lane / Q, q = lane - slot * Q;
-#pragma unroll 2
+#pragma unroll 1
         for (int it = 0; it < ITERS; ++it) {
             const int lr = it * SLOTS + slot;
             const int src = lr < 32 ? lr : 31;
             const int rs = __shfl_sync(kFull, my_s, src) - ibase;
             const int deg = __shfl_sync(kFull, my_deg, src);
-            const int p = wbase + lr;
-            if (slot < SLOTS && lr < 32) {
-                float4 own = make_float4(0.f, 0.f, 0.f, 0.f), cc = own;
-                if (p < n_rows) {
-                    own = ld4(beta_in + (size_t)p * KP + 4 * q);
-                    cc = __ldcs(reinterpret_cast<const float4 *>(h + (size_t)p * KP + 4 * q));
-                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int j0 = 0; j0 < deg; j0 += kNbrUnroll) {
-                        int nb[kNbrUnroll];
-#pragma unroll
-                        for (int u = 0; u < kNbrUnroll; ++u)
-                            nb[u] = j0 + u < deg ? (staged ? iw[rs + j0 + u] : __ldg(indices + ibase + rs + j0 + u)) : -1;
-                        float4 v[kNbrUnroll];
-#pragma unroll
-                        for (int u = 0; u < kNbrUnroll; ++u)
-                            v[u] = nb[u] >= 0 ? ld4(beta_in + (size_t)nb[u] * KP + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                        for (int u = 0; u < kNbrUnroll; ++u) add4(acc, v[u]);
-                    }
-                    if (deg > 0) {
-                        cc.x = fmaf(lam, acc.x, cc.x); cc.y = fmaf(lam, acc.y, cc.y);
-                        cc.z = fmaf(lam, acc.z, cc.z); cc.w = fmaf(lam, acc.w, cc.w);
-                    }
-                }
-                st4(cw + lr * S + 4 * q, cc);
-                st4(bw + lr * S + 4 * q, own);
+            const bool active = slot < SLOTS && lr < 32;
+            const int trow = wrow + (active ? lr : 0);                       // tile row (clamped for idle lanes)
+            const bool live = active && tile_base + trow < n_rows;
+            const int trip = __reduce_max_sync(kFull, live ? deg : 0);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int u = 0; u < trip; ++u) {
+                // absent neighbours read the spot's own staged row with weight 0: no divergent branches
+                const bool has = live && u < deg;
+                int rel = trow;
+                if (has) rel = (staged ? iw[rs + u] : __ldg(indices + ibase + rs + u)) - tile_base;
+                float4 v;
+                if ((unsigned)rel < (unsigned)TILE) v = ld4(b_tile + L::at(rel, q));
+                else v = ld4(beta_in + (size_t)(rel + tile_base) * KP + 4 * q);
+                const float m = has ? 1.f : 0.f;
+                acc.x = fmaf(v.x, m, acc.x); acc.y = fmaf(v.y, m, acc.y);
+                acc.z = fmaf(v.z, m, acc.z); acc.w = fmaf(v.w, m, acc.w);
+            }
+            if (live && deg > 0) {
+                float4 cc = ld4(c_tile + L::at(trow, q));
+                cc.x = fmaf(lam, acc.x, cc.x); cc.y = fmaf(lam, acc.y, cc.y);
+                cc.z = fmaf(lam, acc.z, cc.z); cc.w = fmaf(lam, acc.w, cc.w);
+                st4(c_tile + L::at(trow, q), cc);
             }
         }
     }
     __syncwarp();
 
-    // ---------------- phase B: one spot per lane, cyclic coordinate descent in the direct form
+    // ---------------- step 3: one spot per lane, cyclic coordinate descent in the direct form
     //   part_k = c_k - sum_{j != k} G_kj b_j   (b_j already updated for j < k)
     // G.g holds the NEGATED Gram with a zero diagonal, so step k is Kp/2 packed FFMA2 (fma.rn.f32x2, two
     // fp32 FMAs per issue slot on sm_100) whose G operand pair comes from the constant bank via LDCU.128.
     float dmax = 0.f, amax = 0.f;
     {
+        const int trow = wrow + lane;
         const float lam_deg = lam * (float)my_deg;
         float2 b2[KP / 2];
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
-            const float4 b4 = ld4(bw + lane * S + 4 * q);
+            const float4 b4 = ld4(b_tile + L::at(trow, q));
             b2[2 * q] = make_float2(b4.x, b4.y);
             b2[2 * q + 1] = make_float2(b4.z, b4.w);
         }
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
-            const float4 c4 = ld4(cw + lane * S + 4 * q);
+            const float4 c4 = ld4(c_tile + L::at(trow, q));
             float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -204,18 +230,19 @@ bcd_sweep_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP
                 if (k & 1) b2[k / 2].y = nv; else b2[k / 2].x = nv;
                 set_elem(n4, j, nv);
             }
-            st4(bw + lane * S + 4 * q, n4);
+            st4(c_tile + L::at(trow, q), n4);                        // beta_new replaces c; beta_old stays readable
         }
         if (my_row >= n_rows) { dmax = 0.f; amax = 0.f; }
     }
     __syncwarp();
 
-    // ---------------- phase C: stream the warp's new rows out
+    // ---------------- step 4: stream the warp's new rows out
 #pragma unroll
     for (int i = 0; i < Q; ++i) {
         const int idx = lane + 32 * i;
         const int lr = idx / Q, q = idx - lr * Q;
-        if (wbase + lr < n_rows) st4(beta_out + (size_t)(wbase + lr) * KP + 4 * q, ld4(bw + lr * S + 4 * q));
+        const int p = tile_base + wrow + lr;
+        if (p < n_rows) st4(beta_out + (size_t)p * KP + 4 * q, ld4(c_tile + L::at(wrow + lr, q)));
     }
 
     // ---------------- convergence statistics
@@ -226,7 +253,7 @@ bcd_sweep_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP
     if (threadIdx.x == 0) {
         unsigned bd = 0u, ba = 0u;
 #pragma unroll
-        for (int w = 0; w < kSweepThreads / 32; ++w) { bd = max(bd, red[0][w]); ba = max(ba, red[1][w]); }
+        for (int w = 0; w < NW; ++w) { bd = max(bd, red[0][w]); ba = max(ba, red[1][w]); }
         if (bd > *reinterpret_cast<volatile unsigned *>(&state->max_diff_bits)) atomicMax(&state->max_diff_bits, bd);
         if (ba > *reinterpret_cast<volatile unsigned *>(&state->max_abs_bits)) atomicMax(&state->max_abs_bits, ba);
         if (finalize) {
@@ -485,8 +512,8 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
     for (int k = 0; k < KP; ++k) G.diag[k] = k < n_types ? host_gram[k * n_types + k] : 0.f;
     for (int k = 0; k < n_types; ++k)
         for (int a = 0; a < n_types; ++a) G.g[k * KP + a] = (a == k) ? 0.f : -host_gram[k * n_types + a];
-    static const bool use_v2 = getenv("FDB_SWEEP_V2") != nullptr;
-    if (!use_v2) {
+    static const bool use_ws = getenv("FDB_SWEEP_WS") != nullptr;
+    if (use_ws) {
         using L = WsLayout<KP>;
         static int ctas_per_sm = 0;
         if (!ctas_per_sm) {
@@ -504,16 +531,16 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
         FDB_LAUNCH_CHECK("bcd_sweep_ws_kernel");
         return FDB_OK;
     }
-    const int grid = (int)ceil_div(n_rows, kSweepThreads);
-    constexpr int S = ((KP / 4) % 2 == 1) ? KP : KP + 4;
-    constexpr size_t smem = (size_t)kSweepThreads * 2 * S * 4 + (size_t)(kSweepThreads / 32) * kIdxCap * 4;
+    constexpr int NW = KP <= 32 ? 8 : 4;                   // 256-spot patches (128 for wide rows: smem)
+    constexpr size_t smem = (size_t)NW * 32 * 2 * TileLayout<KP>::S * 4 + (size_t)NW * kIdxCap * 4;
     static bool configured = false;              // per instantiation
     if (!configured) {
-        FDB_CUDA(cudaFuncSetAttribute(bcd_sweep_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FDB_CUDA(cudaFuncSetAttribute(bcd_sweep_kernel<KP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    bcd_sweep_kernel<KP><<<grid, kSweepThreads, smem, st>>>(h, G, beta_in, beta_out, indptr, indices, (int)n_rows,
-                                                         n_types, lam, rho, tol, finalize, state);
+    const int grid = (int)ceil_div(n_rows, NW * 32);
+    bcd_sweep_kernel<KP, NW><<<grid, NW * 32, smem, st>>>(h, G, beta_in, beta_out, indptr, indices, (int)n_rows,
+                                                          n_types, lam, rho, tol, finalize, state);
     FDB_LAUNCH_CHECK("bcd_sweep_kernel");
     return FDB_OK;
 }

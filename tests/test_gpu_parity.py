@@ -129,7 +129,7 @@ def test_fused_sketch_ragged_vs_oracle(fo, monkeypatch, n, G, K, d, density, fra
 
 
 def test_sweep_kernel_variants_agree(monkeypatch):
-    """warp-specialised persistent sweep (default) == one-CTA-per-tile sweep (FDB_SWEEP_V2), bit for bit"""
+    """tile-cached sweep (default) == warp-specialised persistent sweep (FDB_SWEEP_WS), bit for bit"""
     import subprocess, sys, os
     from conftest import ROOT
     code = ("import numpy as np, hashlib, sys; sys.path.insert(0, %r);"
@@ -140,7 +140,7 @@ def test_sweep_kernel_variants_agree(monkeypatch):
             "b, info = bcd_solve(Ys, Xs, A, lambda_=1.0, rho=0.01, max_iter=20, tol=1e-12);"
             "print(hashlib.sha256(b.tobytes()).hexdigest(), info['n_iterations'])" % ROOT)
     outs = []
-    for env_extra in ({}, {"FDB_SWEEP_V2": "1"}):
+    for env_extra in ({}, {"FDB_SWEEP_WS": "1"}):
         env = dict(os.environ, **env_extra)
         outs.append(subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300))
     assert outs[0].returncode == 0 and outs[1].returncode == 0, outs[0].stderr + outs[1].stderr
