@@ -98,19 +98,20 @@ struct TileLayout {
 // (tile order => a compact patch of the tissue).
 //   step 1  the CTA streams its TILE beta_old rows and H rows into shared memory with fully
 //           independent coalesced 128-bit loads (one global round trip, 2*Kp/4 loads in flight per thread);
-//   step 2  neighbour sums: groups of Kp/4 lanes walk a spot's neighbour list; a neighbour inside the
-//           CTA's patch (75-85 % of them) is read from the shared tile, the rest from global/L2;
+//   step 2  neighbour sums, one spot per lane: a neighbour inside the CTA's patch (75-85 % of them) is
+//           read from the shared tile, the rest from global/L2, through the same generic 128-bit loads;
 //           c = H + lam * sum is left in shared memory;
 //   step 3  one spot per lane: cyclic coordinate descent in the direct form on packed FFMA2;
 //   step 4  the warp streams its 32 new rows back out.
 template <int KP, int NW>
-__global__ void __launch_bounds__(NW * 32)
+__global__ void __launch_bounds__(NW * 32, (KP <= 32 ? 3 : 1))
 bcd_sweep_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP> G,
                  const float *__restrict__ beta_in, float *__restrict__ beta_out,
                  const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                  int n_rows, int n_types, float lam, float rho, float tol, int finalize, SolveState *state)
 {
-    if (*reinterpret_cast<volatile int *>(&state->converged)) return;
+    // the flag load overlaps the tile loads below; nothing is written to global memory before it is tested
+    const int already_converged = *reinterpret_cast<volatile int *>(&state->converged);
 
     using L = TileLayout<KP>;
     constexpr int Q = L::Q, S = L::S, TILE = NW * 32;
@@ -151,39 +152,43 @@ bcd_sweep_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP
         for (int t = lane; t < icnt; t += 32) iw[t] = __ldg(indices + ibase + t);
     __syncthreads();
 
-    // ---------------- step 2: c += lam * sum_j beta_old[j]
+    if (already_converged) return;                        // uniform across the grid
+
+    // ---------------- step 2: c += lam * sum_j beta_old[j], one spot per lane.
+    // A neighbour inside the CTA's patch is read from the staged tile, any other from global/L2; the
+    // two cases share one instruction stream through generic 128-bit loads.  Lanes whose list is
+    // shorter than the warp's longest re-read their own staged row with weight 0 (no divergence).
     {
-        const int slot = lane / Q, q = lane - slot * Q;
+        const int trow = wrow + lane;
+        float ns[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) ns[k] = 0.f;
+        const int maxdeg = __reduce_max_sync(kFull, my_deg);
+        const int rs = my_s - ibase;
 #pragma unroll 1
-        for (int it = 0; it < ITERS; ++it) {
-            const int lr = it * SLOTS + slot;
-            const int src = lr < 32 ? lr : 31;
-            const int rs = __shfl_sync(kFull, my_s, src) - ibase;
-            const int deg = __shfl_sync(kFull, my_deg, src);
-            const bool active = slot < SLOTS && lr < 32;
-            const int trow = wrow + (active ? lr : 0);                       // tile row (clamped for idle lanes)
-            const bool live = active && tile_base + trow < n_rows;
-            const int trip = __reduce_max_sync(kFull, live ? deg : 0);
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-            for (int u = 0; u < trip; ++u) {
-                // absent neighbours read the spot's own staged row with weight 0: no divergent branches
-                const bool has = live && u < deg;
-                int rel = trow;
-                if (has) rel = (staged ? iw[rs + u] : __ldg(indices + ibase + rs + u)) - tile_base;
-                float4 v;
-                if ((unsigned)rel < (unsigned)TILE) v = ld4(b_tile + L::at(rel, q));
-                else v = ld4(beta_in + (size_t)(rel + tile_base) * KP + 4 * q);
-                const float m = has ? 1.f : 0.f;
-                acc.x = fmaf(v.x, m, acc.x); acc.y = fmaf(v.y, m, acc.y);
-                acc.z = fmaf(v.z, m, acc.z); acc.w = fmaf(v.w, m, acc.w);
+        for (int u = 0; u < maxdeg; ++u) {
+            const bool has = u < my_deg;
+            int rel = trow;
+            if (has) rel = (staged ? iw[rs + u] : __ldg(indices + my_s + u)) - tile_base;
+            const bool in = (unsigned)rel < (unsigned)TILE;
+            const float *base = in ? (b_tile + rel * S) : (beta_in + (size_t)(rel + tile_base) * KP);
+            const int sw = (L::SWZ && in) ? (rel & 7) : 0;
+            const float m = has ? 1.f : 0.f;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                const float4 v = *reinterpret_cast<const float4 *>(base + 4 * (q ^ sw));
+                ns[4 * q] = fmaf(v.x, m, ns[4 * q]);
+                ns[4 * q + 1] = fmaf(v.y, m, ns[4 * q + 1]);
+                ns[4 * q + 2] = fmaf(v.z, m, ns[4 * q + 2]);
+                ns[4 * q + 3] = fmaf(v.w, m, ns[4 * q + 3]);
             }
-            if (live && deg > 0) {
-                float4 cc = ld4(c_tile + L::at(trow, q));
-                cc.x = fmaf(lam, acc.x, cc.x); cc.y = fmaf(lam, acc.y, cc.y);
-                cc.z = fmaf(lam, acc.z, cc.z); cc.w = fmaf(lam, acc.w, cc.w);
-                st4(c_tile + L::at(trow, q), cc);
-            }
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            float4 cc = ld4(c_tile + L::at(trow, q));
+            cc.x = fmaf(lam, ns[4 * q], cc.x); cc.y = fmaf(lam, ns[4 * q + 1], cc.y);
+            cc.z = fmaf(lam, ns[4 * q + 2], cc.z); cc.w = fmaf(lam, ns[4 * q + 3], cc.w);
+            st4(c_tile + L::at(trow, q), cc);
         }
     }
     __syncwarp();
@@ -220,11 +225,8 @@ bcd_sweep_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP
                 const float part = (a0.x + a0.y) + (a1.x + a1.y);
                 const float old = (k & 1) ? b2[k / 2].y : b2[k / 2].x;
                 const float den = G.diag[k] + lam_deg;
-                float nv = 0.f;
-                if (den > 1e-10f) {
-                    const float sh = part > rho ? part - rho : (part < -rho ? part + rho : 0.f);
-                    nv = fmaxf(0.f, __fdividef(sh, den));
-                }
+                // max(0, soft(part, rho) / den) == max(0, (part - rho) / den) for den > 0
+                const float nv = den > 1e-10f ? fmaxf(0.f, __fdividef(part - rho, den)) : 0.f;
                 dmax = fmaxf(dmax, fabsf(nv - old));
                 amax = fmaxf(amax, fabsf(old));
                 if (k & 1) b2[k / 2].y = nv; else b2[k / 2].x = nv;
