@@ -42,6 +42,22 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def profiled_traffic(config, kernel_prefix):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (profiles/), or None."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    try:
+        for name in sorted(os.listdir(pdir)):
+            if name.endswith(f"_traffic_{config}.json"):
+                with open(os.path.join(pdir, name)) as f:
+                    for k, v in json.load(f)["dram_bytes_per_launch"].items():
+                        if k.startswith(kernel_prefix):
+                            best = float(v)
+    except Exception:
+        pass
+    return best
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -267,7 +283,8 @@ def main():
         "gpu_launches": int(launches),
         "stage_ms": stage_ms,
         "roofline": {"bound": "hbm", "kernel": "bcd_sweep_kernel", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic(args.config, "bcd_sweep_kernel"),
+                     "peak_source": peak_src,
                      "bytes_per_launch": sweep_bytes, "ms_per_launch": sweep_ms,
                      "sketch_kernel": {"achieved": sketch_gbs, "frac": sketch_gbs / peak,
                                        "bytes_per_launch": sketch_bytes, "ms_per_launch": stage_ms["sketch"]}},

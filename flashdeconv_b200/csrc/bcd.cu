@@ -103,8 +103,8 @@ struct TileLayout {
 //           c = H + lam * sum is left in shared memory;
 //   step 3  one spot per lane: cyclic coordinate descent in the direct form on packed FFMA2;
 //   step 4  the warp streams its 32 new rows back out.
-template <int KP, int NW>
-__global__ void __launch_bounds__(NW * 32, (KP <= 32 ? 3 : 1))
+template <int KP, int NW, int UNR>
+__global__ void __launch_bounds__(NW * 32, (KP <= 32 ? (UNR == 1 ? 768 / (NW * 32) : 512 / (NW * 32)) : 1))
 bcd_sweep_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP> G,
                  const float *__restrict__ beta_in, float *__restrict__ beta_out,
                  const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
@@ -165,7 +165,7 @@ bcd_sweep_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP
         for (int k = 0; k < KP; ++k) ns[k] = 0.f;
         const int maxdeg = __reduce_max_sync(kFull, my_deg);
         const int rs = my_s - ibase;
-#pragma unroll 1
+#pragma unroll UNR
         for (int u = 0; u < maxdeg; ++u) {
             const bool has = u < my_deg;
             int rel = trow;
@@ -533,18 +533,25 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
         FDB_LAUNCH_CHECK("bcd_sweep_ws_kernel");
         return FDB_OK;
     }
-    constexpr int NW = KP <= 32 ? 8 : 4;                   // 256-spot patches (128 for wide rows: smem)
-    constexpr size_t smem = (size_t)NW * 32 * 2 * TileLayout<KP>::S * 4 + (size_t)NW * kIdxCap * 4;
-    static bool configured = false;              // per instantiation
-    if (!configured) {
-        FDB_CUDA(cudaFuncSetAttribute(bcd_sweep_kernel<KP, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+    // tile size / gather unroll: production default first, the others are tuning variants (FDB_SWEEP_VARIANT)
+    static const int variant = getenv("FDB_SWEEP_VARIANT") ? atoi(getenv("FDB_SWEEP_VARIANT")) : 0;
+    auto go = [&](auto kern, int nw) -> int {
+        const size_t smem = (size_t)nw * 32 * 2 * TileLayout<KP>::S * 4 + (size_t)nw * kIdxCap * 4;
+        FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = (int)ceil_div(n_rows, nw * 32);
+        kern<<<grid, nw * 32, smem, st>>>(h, G, beta_in, beta_out, indptr, indices, (int)n_rows, n_types, lam, rho,
+                                          tol, finalize, state);
+        FDB_LAUNCH_CHECK("bcd_sweep_kernel");
+        return FDB_OK;
+    };
+    if constexpr (KP <= 32) {
+        if (variant == 1) return go(bcd_sweep_kernel<KP, 4, 1>, 4);
+        if (variant == 2) return go(bcd_sweep_kernel<KP, 8, 2>, 8);
+        if (variant == 3) return go(bcd_sweep_kernel<KP, 4, 2>, 4);
+        return go(bcd_sweep_kernel<KP, 8, 1>, 8);
+    } else {
+        return go(bcd_sweep_kernel<KP, 4, 1>, 4);
     }
-    const int grid = (int)ceil_div(n_rows, NW * 32);
-    bcd_sweep_kernel<KP, NW><<<grid, NW * 32, smem, st>>>(h, G, beta_in, beta_out, indptr, indices, (int)n_rows,
-                                                          n_types, lam, rho, tol, finalize, state);
-    FDB_LAUNCH_CHECK("bcd_sweep_kernel");
-    return FDB_OK;
 }
 
 static int dispatch_sweep(const float *h, const float *host_gram, int n_types, const float *beta_in,
