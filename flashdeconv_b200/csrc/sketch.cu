@@ -117,8 +117,8 @@ sketch_contract_kernel(const IndPtr *__restrict__ indptr, const int32_t *__restr
                        const int32_t *__restrict__ gene_bucket,
                        const float *__restrict__ gene_weight, int d,
                        const float *__restrict__ x_sketch_t, int kp,
-                       const int32_t *__restrict__ row_map, float *__restrict__ h,
-                       float *__restrict__ ysq)
+                       const int32_t *__restrict__ row_map, const int32_t *__restrict__ row_ids,
+                       float *__restrict__ h, float *__restrict__ ysq)
 {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31;
@@ -135,8 +135,9 @@ sketch_contract_kernel(const IndPtr *__restrict__ indptr, const int32_t *__restr
     __syncthreads();
 
     RowCache rc;
-    for (int64_t row = (int64_t)blockIdx.x * warps_per_cta + warp; row < n_spots;
-         row += (int64_t)gridDim.x * warps_per_cta) {
+    for (int64_t it = (int64_t)blockIdx.x * warps_per_cta + warp; it < n_spots;
+         it += (int64_t)gridDim.x * warps_per_cta) {
+        const int64_t row = row_ids ? (int64_t)__ldg(row_ids + it) : it;       // input row processed by this warp
         const int64_t s = load_ptr(indptr, row), e = load_ptr(indptr, row + 1);
         const float scale = 1e4f / row_pass1(indices, counts, gene_bucket, gene_weight, s, e, lane, rc);
         float h0 = 0.f, h1 = 0.f;
@@ -177,7 +178,7 @@ sketch_contract_kernel(const IndPtr *__restrict__ indptr, const int32_t *__restr
             sq = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, sq))));
         }
         sq = warp_sum(sq);
-        const int64_t orow = row_map ? (int64_t)__ldg(row_map + row) : row;
+        const int64_t orow = row_map ? (int64_t)__ldg(row_map + row) : it;
         float *out = h + orow * kp;
         if (lane < kp) out[lane] = h0;
         if (NK == 2 && 32 + lane < kp) out[32 + lane] = h1;
@@ -226,7 +227,8 @@ sketch_contract_v2_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
                           const float *__restrict__ counts, int64_t n_spots, int n_genes,
                           const int32_t *__restrict__ gene_bucket, const float *__restrict__ gene_weight,
                           int d, const float *__restrict__ x_sketch_t, int kp,
-                          const int32_t *__restrict__ row_map, float *__restrict__ h, float *__restrict__ ysq)
+                          const int32_t *__restrict__ row_map, const int32_t *__restrict__ row_ids,
+                          float *__restrict__ h, float *__restrict__ ysq)
 {
     constexpr int XR = NK * 32 + 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -256,8 +258,9 @@ sketch_contract_v2_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
     unsigned lt_mask;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
 
-    for (int64_t row = (int64_t)blockIdx.x * warps_per_cta + warp; row < n_spots;
-         row += (int64_t)gridDim.x * warps_per_cta) {
+    for (int64_t it = (int64_t)blockIdx.x * warps_per_cta + warp; it < n_spots;
+         it += (int64_t)gridDim.x * warps_per_cta) {
+        const int64_t row = row_ids ? (int64_t)__ldg(row_ids + it) : it;       // input row processed by this warp
         const int64_t s = load_ptr(indptr, row), e = load_ptr(indptr, row + 1);
         float hv[NK * 32];
 #pragma unroll
@@ -345,7 +348,7 @@ sketch_contract_v2_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
             sq = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, sq))));
         }
         sq = warp_sum(sq);
-        const int64_t orow = row_map ? (int64_t)__ldg(row_map + row) : row;
+        const int64_t orow = row_map ? (int64_t)__ldg(row_map + row) : it;
         float *out = h + orow * kp;
         if (lane < kp) out[lane] = hv[0];
         if (NK == 2 && 32 + lane < kp) out[32 + lane] = hv[1];
@@ -495,8 +498,8 @@ extern "C" __attribute__((visibility("default"))) int fdb_contract(const float *
 template <typename IndPtr, int NK>
 static int launch_fused(const void *indptr, const int32_t *indices, const float *counts,
                         int64_t n_spots, int n_genes, const int32_t *gene_bucket, const float *gene_weight,
-                        int d, const float *x_sketch_t, int kp, const int32_t *row_map, float *h, float *ysq,
-                        cudaStream_t st)
+                        int d, const float *x_sketch_t, int kp, const int32_t *row_map, const int32_t *row_ids, float *h,
+                        float *ysq, cudaStream_t st)
 {
     // preferred: v2 (tables + compaction lists in shared memory), one 16/12/8/4-warp CTA per SM
     {
@@ -512,7 +515,7 @@ static int launch_fused(const void *indptr, const int32_t *indices, const float 
             FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const int grid = pick_grid(n_spots, warps, 1);
             kern<<<grid, warps * 32, smem, st>>>((const IndPtr *)indptr, indices, counts, n_spots, n_genes,
-                                                 gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, h, ysq);
+                                                 gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq);
             FDB_LAUNCH_CHECK("sketch_contract_v2_kernel");
             return FDB_OK;
         }
@@ -537,7 +540,7 @@ static int launch_fused(const void *indptr, const int32_t *indices, const float 
     FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = pick_grid(n_spots, warps, per_sm);
     kern<<<grid, warps * 32, smem, st>>>((const IndPtr *)indptr, indices, counts, n_spots, gene_bucket,
-                                         gene_weight, d, x_sketch_t, kp, row_map, h, ysq);
+                                         gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq);
     FDB_LAUNCH_CHECK("sketch_contract_kernel");
     return FDB_OK;
 }
@@ -546,7 +549,7 @@ extern "C" __attribute__((visibility("default"))) int fdb_sketch_contract_csr(co
                                        const float *counts, int64_t n_spots, int32_t n_genes,
                                        const int32_t *gene_bucket, const float *gene_weight, int32_t d,
                                        const float *x_sketch_t, int32_t n_types, const int32_t *row_map,
-                                       float *h, float *ysq, void *stream)
+                                       const int32_t *row_ids, float *h, float *ysq, void *stream)
 {
     FDB_REQUIRE(n_spots >= 0 && n_genes >= 0, "negative shape");
     FDB_REQUIRE(d > 0 && d % 4 == 0, "sketch_dim must be a positive multiple of 4, got %d", d);
@@ -557,11 +560,11 @@ extern "C" __attribute__((visibility("default"))) int fdb_sketch_contract_csr(co
     cudaStream_t st = (cudaStream_t)stream;
     if (kp <= 32)
         return indptr_is_int64
-                   ? launch_fused<int64_t, 1>(indptr, indices, counts, n_spots, n_genes, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, h, ysq, st)
-                   : launch_fused<int32_t, 1>(indptr, indices, counts, n_spots, n_genes, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, h, ysq, st);
+                   ? launch_fused<int64_t, 1>(indptr, indices, counts, n_spots, n_genes, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, st)
+                   : launch_fused<int32_t, 1>(indptr, indices, counts, n_spots, n_genes, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, st);
     return indptr_is_int64
-               ? launch_fused<int64_t, 2>(indptr, indices, counts, n_spots, n_genes, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, h, ysq, st)
-               : launch_fused<int32_t, 2>(indptr, indices, counts, n_spots, n_genes, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, h, ysq, st);
+               ? launch_fused<int64_t, 2>(indptr, indices, counts, n_spots, n_genes, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, st)
+               : launch_fused<int32_t, 2>(indptr, indices, counts, n_spots, n_genes, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, st);
 }
 
 extern "C" __attribute__((visibility("default"))) int fdb_gene_moments_csr(const void *indptr, int indptr_is_int64, const int32_t *indices,

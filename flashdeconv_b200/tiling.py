@@ -1,0 +1,303 @@
+"""Multi-GPU partition of the hot path: spatial tiles + per-sweep halo exchange.
+
+The reference is single-process; this module is the B200-native scale-out of its Jacobi
+sweep.  Because every sweep reads only the PREVIOUS iterate of a spot's neighbours (core/solver.py:161-166),
+cutting the spots into R tiles changes nothing but the order of float additions:
+
+  * tile order (graph.cu) is a spatially coherent numbering, so rank r owns the contiguous position range
+    [lo_r, hi_r) -- a compact patch of the tissue -- and sketches / solves only those rows;
+  * neighbours owned by another rank become HALO rows appended after the rank's own rows in its beta buffers
+    (sorted by global position, hence grouped by owner: a peer's rows land in one contiguous slice, no unpack);
+  * per sweep: sweep own rows -> pack the boundary rows each peer needs (fdb_rows_gather) -> batched
+    isend/irecv over NCCL/NVLink straight into the halo slices -> MAX all-reduce of the two max-norm words
+    (the reference's stop test uses global max norms, core/solver.py:395-397) -> fdb_bcd_finalize;
+  * X_s, the Gram matrix, lambda, rho and the (small) graph are replicated: every rank builds the full graph
+    from the replicated coordinates (0.7 ms at 1M spots) instead of exchanging k-NN lists.
+
+`plan_tile` / `halo_exchange` are device-agnostic torch code so that the partition logic is tested on CPU with
+the gloo backend (tests/test_tiling_gloo.py); `TiledPath` is the GPU driver.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+
+
+def tile_bounds(n: int, world: int, align: int = 256) -> List[Tuple[int, int]]:
+    """Contiguous position ranges, one per rank, cut at multiples of `align` (the sweep kernel's CTA tile)."""
+    if world <= 0:
+        raise ValueError("world must be positive")
+    blocks = -(-n // align)
+    cuts = [min(n, ((blocks * r) // world) * align) for r in range(world)] + [n]
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+@dataclass
+class TilePlan:
+    rank: int
+    lo: int
+    hi: int
+    n_own: int
+    n_halo: int
+    indptr: "object"               # int32[n_own + 1], local
+    indices: "object"              # int32[nnz_local], local numbering: own rows 0..n_own-1, halo rows after
+    halo_global: "object"          # int64[n_halo] global positions of the halo rows (ascending)
+    recv: List[Tuple[int, int, int]]        # (peer, first halo slot, count)
+    send: List[Tuple[int, "object"]]        # (peer, int32 local row ids to send, ascending global position)
+
+    @property
+    def n_total(self) -> int:
+        return self.n_own + self.n_halo
+
+
+def plan_tile(indptr, indices, bounds: List[Tuple[int, int]], rank: int) -> TilePlan:
+    """Local adjacency + halo maps for `rank` from the replicated global CSR (torch tensors, any device)."""
+    import torch
+    lo, hi = bounds[rank]
+    dev = indices.device
+    ip = indptr.to(torch.int64)
+    e0, e1 = int(ip[lo]), int(ip[hi])
+    nbr = indices[e0:e1].to(torch.int64)
+    outside = (nbr < lo) | (nbr >= hi)
+    halo_global = torch.unique(nbr[outside])                       # sorted ascending
+    n_own, n_halo = hi - lo, int(halo_global.numel())
+    local = nbr - lo
+    if n_halo:
+        local = torch.where(outside, n_own + torch.searchsorted(halo_global, nbr), local)
+    recv, send = [], []
+    starts = torch.tensor([b[0] for b in bounds] + [bounds[-1][1]], device=dev, dtype=torch.int64)
+    if n_halo:
+        owner_edges = torch.searchsorted(halo_global, starts)       # halo rows are grouped by owner
+        for peer in range(len(bounds)):
+            a, b = int(owner_edges[peer]), int(owner_edges[peer + 1])
+            if peer != rank and b > a:
+                recv.append((peer, a, b - a))
+    for peer, (plo, phi) in enumerate(bounds):
+        if peer == rank or phi <= plo:
+            continue
+        pe0, pe1 = int(ip[plo]), int(ip[phi])
+        pn = indices[pe0:pe1].to(torch.int64)
+        mine = torch.unique(pn[(pn >= lo) & (pn < hi)])             # what `peer` needs from me, ascending
+        if mine.numel():
+            send.append((peer, (mine - lo).to(torch.int32).contiguous()))
+    return TilePlan(rank, lo, hi, n_own, n_halo, (ip[lo:hi + 1] - e0).to(torch.int32).contiguous(),
+                    local.to(torch.int32).contiguous(), halo_global, recv, send)
+
+
+def halo_exchange(beta, plan: TilePlan, pack: Callable, group=None, tag: int = 0):
+    """Fill the halo rows of `beta` (n_total x row_floats) with the owners' current rows.
+
+    pack(beta, row_ids) -> contiguous (len(row_ids) x row_floats) tensor of the rows to send."""
+    import torch.distributed as dist
+    ops, keep = [], []
+    for peer, first, count in plan.recv:
+        ops.append(dist.P2POp(dist.irecv, beta[plan.n_own + first: plan.n_own + first + count], peer, group))
+    for peer, rows in plan.send:
+        buf = pack(beta, rows)
+        keep.append(buf)
+        ops.append(dist.P2POp(dist.isend, buf, peer, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return keep
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU driver
+# ----------------------------------------------------------------------------------------------------
+class TiledPath:
+    """One rank's share of a deconvolution partitioned over the ranks of a torch.distributed group.
+
+    Every rank passes the SAME full inputs (replicated CSR / coords) or at least every CSR row of its own tile;
+    only the rank's tile is sketched and solved.  Results stay sharded on the device (`beta_own`, in tile
+    order) until `gather_outputs` assembles float64 arrays in input order on every rank."""
+
+    def __init__(self, csr, coords_dev, tables, n_types: int, group=None):
+        import torch
+        import torch.distributed as dist
+        from . import _native, pipeline
+        self.torch, self.dist, self.pl = torch, dist, pipeline
+        self.lib, self.check = _native.lib, _native.check
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.csr, self.coords, self.tables, self.K = csr, coords_dev, tables, int(n_types)
+        self.Kp = _native.padded_types(self.K)
+        self.dev = csr.indices.device
+        self.gene_bucket = torch.from_numpy(tables.gene_bucket).to(self.dev)
+        self.gene_weight = torch.from_numpy(tables.gene_weight).to(self.dev)
+        xst = np.zeros((tables.d, self.Kp), dtype=np.float32)
+        xst[:, : self.K] = tables.X_sketch.T
+        self.x_sketch_t = torch.from_numpy(xst).to(self.dev)
+        self.gram32 = np.ascontiguousarray(tables.gram, dtype=np.float32)
+        self.state = torch.zeros(16, dtype=torch.int32, device=self.dev)
+        self.graph = None
+        self.plan: Optional[TilePlan] = None
+
+    def _stream(self):
+        return self.pl._stream(self.torch)
+
+    def stage_graph(self, method="knn", k=6, radius=None):
+        pl, t = self.pl, self.torch
+        self.graph = pl.build_graph(self.coords, method, k, radius)       # replicated, deterministic
+        n = int(self.graph.order.numel())
+        self.bounds = tile_bounds(n, self.world)
+        self.plan = plan_tile(self.graph.indptr, self.graph.indices[: max(self.graph.nnz, 1)], self.bounds, self.rank)
+        p = self.plan
+        if p.indices.numel() == 0:
+            p.indices = t.zeros(1, dtype=t.int32, device=self.dev)
+        self.h = t.empty((max(p.n_own, 1), self.Kp), dtype=t.float32, device=self.dev)
+        self.ysq = t.empty(max(p.n_own, 1), dtype=t.float32, device=self.dev)
+        self.beta_a = t.empty((max(p.n_total, 1), self.Kp), dtype=t.float32, device=self.dev)
+        self.beta_b = t.empty((max(p.n_total, 1), self.Kp), dtype=t.float32, device=self.dev)
+        self.send_bufs = [t.empty((rows.numel(), self.Kp), dtype=t.float32, device=self.dev) for _, rows in p.send]
+        return self.graph
+
+    def stage_sketch(self):
+        c, tb, p = self.csr, self.tables, self.plan
+        if p.n_own == 0:
+            return
+        row_ids = self.graph.order[p.lo:p.hi].contiguous()
+        self._row_ids = row_ids
+        self.check(self.lib.fdb_sketch_contract_csr(
+            self.pl._ptr(c.indptr), int(c.indptr.dtype == self.torch.int64), self.pl._ptr(c.indices),
+            self.pl._ptr(c.data), p.n_own, c.shape[1], self.pl._ptr(self.gene_bucket), self.pl._ptr(self.gene_weight),
+            tb.d, self.pl._ptr(self.x_sketch_t), self.K, self.pl._ptr(None), self.pl._ptr(row_ids),
+            self.pl._ptr(self.h), self.pl._ptr(self.ysq), self._stream()), "sketch_contract_csr")
+
+    def lambda_auto(self, alpha=0.005) -> float:
+        n = int(self.graph.order.numel())
+        return float(alpha * float(np.mean(np.diag(self.tables.gram))) / max(self.graph.nnz / max(n, 1), 1.0))
+
+    def rho_scaled(self, rho) -> float:
+        return float(rho) * float(np.mean(np.diag(self.tables.gram)))
+
+    def _pack(self, beta, rows, out):
+        self.check(self.lib.fdb_rows_gather(self.pl._ptr(beta), self.pl._ptr(rows), rows.numel(), self.Kp,
+                                            self.pl._ptr(out), self._stream()), "rows_gather")
+        return out
+
+    def _exchange(self, beta):
+        dist, p = self.dist, self.plan
+        ops = []
+        for peer, first, count in p.recv:
+            ops.append(dist.P2POp(dist.irecv, beta[p.n_own + first: p.n_own + first + count], peer, self.group))
+        for (peer, rows), buf in zip(p.send, self.send_bufs):
+            ops.append(dist.P2POp(dist.isend, self._pack(beta, rows, buf), peer, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def stage_solve(self, lam, rho_scaled, max_iter, tol):
+        """Jacobi sweeps with halo exchange; no host synchronisation inside the loop."""
+        t, p, pl = self.torch, self.plan, self.pl
+        st = self._stream()
+        gram = self.gram32.ctypes.data_as(C.c_void_p)
+        self.check(self.lib.fdb_bcd_init(pl._ptr(self.beta_a), p.n_total, self.K, pl._ptr(self.state), st), "bcd_init")
+        self.check(self.lib.fdb_bcd_init(pl._ptr(self.beta_b), p.n_total, self.K, pl._ptr(None), st), "bcd_init")
+        norms = self.state[:2].view(t.float32)          # max-norm bit patterns of non-negative floats order like floats
+        cur, nxt = self.beta_a, self.beta_b
+        for _ in range(max_iter):
+            if p.n_own:
+                self.check(self.lib.fdb_bcd_sweep(pl._ptr(self.h), gram, pl._ptr(cur), pl._ptr(nxt), pl._ptr(p.indptr),
+                                                  pl._ptr(p.indices), p.n_own, self.K, float(lam), float(rho_scaled),
+                                                  float(tol), 0, pl._ptr(self.state), st), "bcd_sweep")
+            self._exchange(nxt)
+            self.dist.all_reduce(norms, op=self.dist.ReduceOp.MAX, group=self.group)
+            self.check(self.lib.fdb_bcd_finalize(pl._ptr(self.state), float(tol), st), "bcd_finalize")
+            cur, nxt = nxt, cur
+
+    def read_state(self):
+        st = self.state.cpu()
+        return int(st[3]), bool(int(st[4])), float(st[5:6].view(self.torch.float32)[0])
+
+    def current_beta(self, n_iter):
+        return self.beta_a if n_iter % 2 == 0 else self.beta_b
+
+    def objective(self, beta_dev, lam, rho_scaled) -> float:
+        t, p, pl = self.torch, self.plan, self.pl
+        out = t.zeros(5, dtype=t.float64, device=self.dev)
+        if p.n_own:
+            self.check(self.lib.fdb_objective_terms(pl._ptr(beta_dev), pl._ptr(self.h), pl._ptr(self.ysq),
+                                                    self.gram32.ctypes.data_as(C.c_void_p), pl._ptr(p.indptr),
+                                                    pl._ptr(p.indices), p.n_own, self.K, pl._ptr(out), self._stream()),
+                       "objective_terms")
+        self.dist.all_reduce(out, op=self.dist.ReduceOp.SUM, group=self.group)
+        cross, quad, lap, l1, yty = out.cpu().tolist()
+        return 0.5 * (yty - 2.0 * cross + quad) + 0.5 * lam * lap + rho_scaled * l1
+
+    def finish_sharded(self, beta_dev):
+        """float64 beta / proportions for this rank's rows, written at their INPUT-order row of full-size buffers."""
+        t, p, pl = self.torch, self.plan, self.pl
+        n = int(self.graph.order.numel())
+        if not hasattr(self, "_b64"):
+            self._b64 = t.empty((n, self.K), dtype=t.float64, device=self.dev)
+            self._p64 = t.empty((n, self.K), dtype=t.float64, device=self.dev)
+        self._b64.zero_()
+        self._p64.zero_()
+        if p.n_own:
+            self.check(self.lib.fdb_finish(pl._ptr(beta_dev), pl._ptr(self._row_ids), p.n_own, self.K,
+                                           pl._ptr(self._b64), pl._ptr(self._p64), self._stream()), "finish")
+        return self._b64, self._p64
+
+    def gather_outputs(self):
+        """Every rank contributes its rows (zeros elsewhere): one SUM all-reduce assembles the full arrays."""
+        self.dist.all_reduce(self._b64, op=self.dist.ReduceOp.SUM, group=self.group)
+        self.dist.all_reduce(self._p64, op=self.dist.ReduceOp.SUM, group=self.group)
+        return self._b64, self._p64
+
+    def run_resident(self, *, method="knn", k=6, radius=None, lam="auto", rho=0.01, max_iter=100, tol=1e-4,
+                     events=None, gather=False):
+        t = self.torch
+
+        def mark(name, fn):
+            if events is None:
+                return fn()
+            a, b = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
+            a.record()
+            out = fn()
+            b.record()
+            events[name] = (a, b)
+            return out
+
+        mark("graph", lambda: self.stage_graph(method, k, radius))
+        mark("sketch", self.stage_sketch)
+        lam_used = self.lambda_auto() if isinstance(lam, str) else float(lam)
+        rho_s = self.rho_scaled(rho)
+        mark("solve", lambda: self.stage_solve(lam_used, rho_s, max_iter, tol))
+        n_iter, conv, rel = self.read_state()
+        beta_dev = self.current_beta(n_iter)
+        obj = mark("objective", lambda: self.objective(beta_dev, lam_used, rho_s))
+        b64, p64 = mark("finish", lambda: self.finish_sharded(beta_dev))
+        if gather:
+            b64, p64 = self.gather_outputs()
+        info = dict(converged=conv, n_iterations=n_iter, final_objective=obj, objectives=[],
+                    final_change=rel if max_iter else 0.0)
+        return b64, p64, info, lam_used
+
+
+def deconvolve_path_tiled(Y, X, coords, gene_idx, leverage, *, sketch_dim=512, lambda_spatial="auto",
+                          rho_sparsity=0.01, spatial_method="knn", k_neighbors=6, radius=None, max_iter=100,
+                          tol=1e-4, random_state=0, pinned_out=False, group=None):
+    """Multi-GPU counterpart of pipeline.deconvolve_path: every rank passes the same HOST inputs, uploads them,
+    solves its tile and gets the full float64 outputs back (SUM all-reduce of the disjoint row sets)."""
+    import torch
+    from . import pipeline
+    tables = pipeline.build_tables(X, gene_idx, leverage, sketch_dim, random_state, Y.shape[1])
+    csr = pipeline.csr_to_device(Y)
+    c = coords if torch.is_tensor(coords) else torch.from_numpy(np.ascontiguousarray(coords, dtype=np.float64))
+    path = TiledPath(csr, c.to(csr.indices.device, non_blocking=True), tables, np.asarray(X).shape[0], group)
+    b64, p64, info, lam = path.run_resident(method=spatial_method, k=k_neighbors, radius=radius, lam=lambda_spatial,
+                                            rho=rho_sparsity, max_iter=max_iter, tol=tol, gather=True)
+    if pinned_out:
+        hb = torch.empty(b64.shape, dtype=torch.float64, pin_memory=True)
+        hp = torch.empty(p64.shape, dtype=torch.float64, pin_memory=True)
+        hb.copy_(b64, non_blocking=True)
+        hp.copy_(p64, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        beta, prop = hb.numpy(), hp.numpy()
+    else:
+        beta, prop = b64.cpu().numpy(), p64.cpu().numpy()
+    return pipeline.SolveResult(beta, prop, info, lam, path.graph, tables)

@@ -74,14 +74,16 @@ int fdb_contract(const float *y_sketch, const float *x_sketch, int64_t n_spots, 
                  int32_t n_types, float *h, float *ysq, void *stream);
 
 /* (a1 + a3 + a4) production form: never materialises Y_s.  Streams the CSR once and writes
- *   h[row_map ? row_map[i] : i][:] = X_s . y_s,i      (n_spots x Kp, float32)
- *   ysq[row_map ? row_map[i] : i]  = ||y_s,i||^2
+ *   h[out(i)][:] = X_s . y_s,row(i)      (float32, Kp per row)        ysq[out(i)] = ||y_s,row(i)||^2
+ * for i in [0, n_spots), where row(i) = row_ids ? row_ids[i] : i is the CSR row processed and
+ * out(i) = row_map ? row_map[row(i)] : i.  row_map places results in tile order (single GPU);
+ * row_ids selects the rows of one spatial tile (multi-GPU: row_ids = order[lo:hi], out = i).
  * x_sketch_t is the TRANSPOSED sketched reference, d x Kp row-major (padding columns zero). */
 int fdb_sketch_contract_csr(const void *indptr, int indptr_is_int64, const int32_t *indices,
                             const float *counts, int64_t n_spots, int32_t n_genes,
                             const int32_t *gene_bucket, const float *gene_weight, int32_t d,
                             const float *x_sketch_t, int32_t n_types, const int32_t *row_map,
-                            float *h, float *ysq, void *stream);
+                            const int32_t *row_ids, float *h, float *ysq, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * (a5) spatial graph.  Replaces build_knn_graph (utils/graph.py:25-83), build_radius_graph

@@ -354,3 +354,27 @@ def test_fit_variants_behave_like_the_reference_tests():
     assert m.lambda_used_ == 0.5 and m.info_["n_iterations"] == 5
     with pytest.raises(NotImplementedError):
         FlashDeconv(preprocess="pearson").fit(Yd, ds.X, ds.coords)
+
+
+# ---------------------------------------------------------------- multi-GPU tiling (NCCL)
+def _run_tiled(nproc):
+    import os, subprocess, sys
+    from conftest import ROOT
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(29500 + 7 * nproc + os.getpid() % 400),
+           os.path.join(ROOT, "tools", "check_tiled.py"), "20000"]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+
+
+def test_tiled_path_single_rank_equals_device_path():
+    out = _run_tiled(1)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_tiled_path_two_ranks_equals_device_path():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = _run_tiled(2)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "OK" in out.stdout
