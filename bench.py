@@ -241,6 +241,8 @@ def main():
     e2e_kw = dict(sketch_dim=SOLVER["d"], spatial_method=cfg["method"], k_neighbors=SOLVER["k"],
                   rho_sparsity=SOLVER["rho"], max_iter=SOLVER["max_iter"], tol=SOLVER["tol"],
                   random_state=SOLVER["seed"], pinned_out=True)
+    if distributed:
+        path.close()
     del path
     torch.cuda.empty_cache()
     e2e_times = []

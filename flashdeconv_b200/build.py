@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libfdb200.so")
-SOURCES = ["common.cu", "sketch.cu", "graph.cu", "bcd.cu"]
+SOURCES = ["common.cu", "sketch.cu", "graph.cu", "bcd.cu", "comm.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -59,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(one, SOURCES))
-    link = [nvcc, "-shared", *ARCH, "-o", LIB + ".tmp", *objs, "-cudart", "static"]
+    link = [nvcc, "-shared", *ARCH, "-o", LIB + ".tmp", *objs, "-cudart", "static", "-ldl"]
     res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")

@@ -135,6 +135,29 @@ class TiledPath:
         self.state = torch.zeros(16, dtype=torch.int32, device=self.dev)
         self.graph = None
         self.plan: Optional[TilePlan] = None
+        self.comm = self._native_comm()
+
+    def _native_comm(self):
+        """NCCL communicator owned by libfdb200 (the solve loop issues its collectives from C).  The unique id
+        travels over the existing torch.distributed group.  FDB_TILED_TORCH=1 keeps everything in torch."""
+        import os
+        if os.environ.get("FDB_TILED_TORCH"):
+            return None
+        buf = C.create_string_buffer(128)
+        if self.rank == 0:
+            self.check(self.lib.fdb_comm_unique_id(buf), "comm_unique_id")
+        box = [buf.raw]
+        self.dist.broadcast_object_list(box, src=self.dist.get_global_rank(self.group, 0) if self.group else 0,
+                                        group=self.group)
+        comm = C.c_void_p()
+        self.check(self.lib.fdb_comm_init(self.rank, self.world, box[0], C.byref(comm)), "comm_init")
+        return comm
+
+    def close(self):
+        if getattr(self, "comm", None):
+            self.torch.cuda.synchronize()
+            self.lib.fdb_comm_destroy(self.comm)
+            self.comm = None
 
     def _stream(self):
         return self.pl._stream(self.torch)
@@ -195,6 +218,22 @@ class TiledPath:
         t, p, pl = self.torch, self.plan, self.pl
         st = self._stream()
         gram = self.gram32.ctypes.data_as(C.c_void_p)
+        if self.comm is not None:
+            i32, i64, vp = C.c_int32, C.c_int64, C.c_void_p
+            nr, ns = len(p.recv), len(p.send)
+            recv_peer = (i32 * max(nr, 1))(*[r[0] for r in p.recv])
+            recv_first = (i64 * max(nr, 1))(*[r[1] for r in p.recv])
+            recv_count = (i64 * max(nr, 1))(*[r[2] for r in p.recv])
+            send_peer = (i32 * max(ns, 1))(*[q for q, _ in p.send])
+            send_rows = (vp * max(ns, 1))(*[rows.data_ptr() for _, rows in p.send])
+            send_count = (i64 * max(ns, 1))(*[rows.numel() for _, rows in p.send])
+            send_buf = (vp * max(ns, 1))(*[b.data_ptr() for b in self.send_bufs])
+            self.check(self.lib.fdb_bcd_solve_tiled(
+                pl._ptr(self.h), gram, pl._ptr(self.beta_a), pl._ptr(self.beta_b), pl._ptr(p.indptr), pl._ptr(p.indices),
+                p.n_own, p.n_total, self.K, float(lam), float(rho_scaled), int(max_iter), float(tol),
+                pl._ptr(self.state), nr, recv_peer, recv_first, recv_count, ns, send_peer, send_rows, send_count,
+                send_buf, self.comm, st), "bcd_solve_tiled")
+            return
         self.check(self.lib.fdb_bcd_init(pl._ptr(self.beta_a), p.n_total, self.K, pl._ptr(self.state), st), "bcd_init")
         self.check(self.lib.fdb_bcd_init(pl._ptr(self.beta_b), p.n_total, self.K, pl._ptr(None), st), "bcd_init")
         norms = self.state[:2].view(t.float32)          # max-norm bit patterns of non-negative floats order like floats
@@ -291,6 +330,7 @@ def deconvolve_path_tiled(Y, X, coords, gene_idx, leverage, *, sketch_dim=512, l
     path = TiledPath(csr, c.to(csr.indices.device, non_blocking=True), tables, np.asarray(X).shape[0], group)
     b64, p64, info, lam = path.run_resident(method=spatial_method, k=k_neighbors, radius=radius, lam=lambda_spatial,
                                             rho=rho_sparsity, max_iter=max_iter, tol=tol, gather=True)
+    path.close()
     if pinned_out:
         hb = torch.empty(b64.shape, dtype=torch.float64, pin_memory=True)
         hp = torch.empty(p64.shape, dtype=torch.float64, pin_memory=True)

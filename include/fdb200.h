@@ -173,6 +173,30 @@ int fdb_gene_moments_csr(const void *indptr, int indptr_is_int64, const int32_t 
                          const float *counts, int64_t n_spots, int32_t n_genes, double *sums,
                          double *sumsq, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Multi-GPU (one process per GPU; no reference counterpart -- the reference is single process).
+ * The communicator is NCCL, bound at run time (dlopen); the 128-byte unique id from rank 0's
+ * fdb_comm_unique_id is distributed by the host layer (torch.distributed, MPI, a file ...).
+ *
+ * fdb_bcd_solve_tiled: the loop of fdb_bcd_solve for one spatial tile.  beta_a / beta_b hold
+ * n_total = n_own + n_halo rows; halo slice [n_own + recv_first[r], +recv_count[r]) is owned by
+ * recv_peer[r]; send_rows[s] (device, int32 local row ids) are the rows send_peer[s] needs, staged
+ * through send_buf[s] (device, send_count[s] x Kp floats).  Per sweep: sweep -> pack -> grouped
+ * ncclSend/ncclRecv -> ncclAllReduce(MAX) of the two max-norm words -> stop test, all on `stream`.
+ * The host_* arrays are HOST arrays (of ints / of device pointers).
+ * ------------------------------------------------------------------------------------- */
+int fdb_comm_unique_id(char *host_id_128);
+int fdb_comm_init(int32_t rank, int32_t world, const char *host_id_128, void **host_comm_out);
+int fdb_comm_destroy(void *comm);
+int fdb_bcd_solve_tiled(const float *h, const float *host_gram, float *beta_a, float *beta_b,
+                        const int32_t *indptr, const int32_t *indices, int64_t n_own, int64_t n_total,
+                        int32_t n_types, float lambda, float rho_scaled, int32_t max_iter, float tol,
+                        void *state, int32_t n_recv, const int32_t *host_recv_peer,
+                        const int64_t *host_recv_first, const int64_t *host_recv_count, int32_t n_send,
+                        const int32_t *host_send_peer, const int32_t *const *host_send_rows,
+                        const int64_t *host_send_count, float *const *host_send_buf, void *comm,
+                        void *stream);
+
 /* Multi-GPU helpers: gather / scatter whole beta rows by index list (halo exchange staging). */
 int fdb_rows_gather(const float *src, const int32_t *rows, int64_t n_list, int32_t row_floats,
                     float *dst, void *stream);

@@ -35,6 +35,7 @@ def main():
           and abs(info["final_objective"] - single.info["final_objective"]) <= 1e-6 * abs(single.info["final_objective"])
           and abs(lam - single.lambda_used) <= 1e-12 * lam)
     halo = tp.plan.n_halo
+    tp.close()
     flags = torch.tensor([int(ok), halo], device="cuda")
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if rank == 0:
