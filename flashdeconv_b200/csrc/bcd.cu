@@ -23,6 +23,7 @@
 //   phase C (coalesced): the warp streams its 32 new rows back out.
 //   Convergence statistics: redux.sync max per warp, one atomicMax per CTA, last CTA finalises.
 #include <algorithm>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include "fdb_common.cuh"
 
@@ -248,6 +249,236 @@ bcd_sweep_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP
     }
 
     // ---------------- convergence statistics
+    const unsigned wd = __reduce_max_sync(kFull, __float_as_uint(dmax));
+    const unsigned wa = __reduce_max_sync(kFull, __float_as_uint(amax));
+    if (lane == 0) { red[0][warp] = wd; red[1][warp] = wa; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned bd = 0u, ba = 0u;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { bd = max(bd, red[0][w]); ba = max(ba, red[1][w]); }
+        if (bd > *reinterpret_cast<volatile unsigned *>(&state->max_diff_bits)) atomicMax(&state->max_diff_bits, bd);
+        if (ba > *reinterpret_cast<volatile unsigned *>(&state->max_abs_bits)) atomicMax(&state->max_abs_bits, ba);
+        if (finalize) {
+            __threadfence();
+            if (atomicAdd(&state->arrived, 1u) == gridDim.x - 1) {
+                __threadfence();
+                finalize_state(state, tol);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Sweep kernel, halo-staged form with a half-precision gather tile (production for Kp % 8 == 0).
+//
+// Same four steps as bcd_sweep_kernel, with the neighbour gather made a pure shared-memory operation:
+//   * the CTA's TILE beta_old rows are staged twice: fp32 (own rows, needed exactly by the descent) and as an
+//     fp16 GATHER tile (64-byte rows for Kp = 32);
+//   * neighbours outside the patch are given a slot in a halo extension of the gather tile (smem atomic
+//     counter), and their rows are then fetched ONCE per CTA with coalesced loads -- instead of every lane
+//     chasing its own 128-byte row through L2 in every round (40 L1 wavefronts per round before);
+//   * the gather reads only fp16 rows from shared memory (4 LDS.128 per neighbour) and accumulates in half2.
+// Why fp16 is admissible for the neighbour sum only: it enters the update as lam*sum with
+// lam*deg ~ 0.5 % of G_kk (core/spatial.py:181-190), so a 5e-4 relative rounding of a neighbour value moves
+// beta by ~1e-7 relative, three orders below the 1e-4 parity bar; the spot's own row, H and the Gram
+// products stay fp32.  (tests/test_gpu_parity.py holds both variants to the same bars.)
+// ------------------------------------------------------------------------------------
+template <int KP, int NW>
+__global__ void __launch_bounds__(NW * 32, 768 / (NW * 32))
+bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP> G,
+                   const float *__restrict__ beta_in, float *__restrict__ beta_out,
+                   const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                   int n_rows, int n_types, float lam, float rho, float tol, int finalize, SolveState *state)
+{
+    static_assert(KP % 8 == 0, "half gather rows need Kp % 8 == 0");
+    const int already_converged = *reinterpret_cast<volatile int *>(&state->converged);
+
+    using L = TileLayout<KP>;
+    constexpr int Q = L::Q, S = L::S, TILE = NW * 32, HCAP = TILE;
+    constexpr int GQ = Q / 2;                            // 16-byte chunks per fp16 gather row
+    constexpr int GROW = KP / 2;                         // 32-bit words per gather row
+    extern __shared__ __align__(16) float sweep_smem[];
+    float *c_tile = sweep_smem;                                                   // TILE x S fp32
+    uint32_t *g_tile = reinterpret_cast<uint32_t *>(sweep_smem + TILE * S);       // (TILE + HCAP) x GROW words
+    int *idx_tile = reinterpret_cast<int *>(g_tile + (TILE + HCAP) * GROW);       // NW x kIdxCap
+    int *halo_src = idx_tile + NW * kIdxCap;                                      // HCAP global row ids
+    __shared__ unsigned red[2][NW];
+    __shared__ int halo_count;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tile_base = blockIdx.x * TILE;
+    const int wrow = warp * 32;
+    int *iw = idx_tile + warp * kIdxCap;
+    if (threadIdx.x == 0) halo_count = 0;
+
+    // ---------------- step 0: row pointers; the warp's beta_old rows go to both tiles (fp32 + fp16)
+    const int my_row = tile_base + wrow + lane;
+    int my_s = 0, my_e = 0;
+    if (my_row < n_rows) { my_s = __ldg(indptr + my_row); my_e = __ldg(indptr + my_row + 1); }
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        const int idx = lane + 32 * i;
+        const int lr = idx / Q, q = idx - lr * Q;
+        const int p = tile_base + wrow + lr;
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p < n_rows) bb = ld4(beta_in + (size_t)p * KP + 4 * q);
+        st4(c_tile + L::at(wrow + lr, q), bb);
+        const __half2 lo = __floats2half2_rn(bb.x, bb.y), hi = __floats2half2_rn(bb.z, bb.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t *>(&lo);
+        pk.y = *reinterpret_cast<const uint32_t *>(&hi);
+        *reinterpret_cast<uint2 *>(g_tile + (wrow + lr) * GROW + 2 * q) = pk;
+    }
+    const int my_deg = my_e - my_s;
+    const int ibase = __shfl_sync(kFull, my_s, 0);
+    const int icnt = __reduce_max_sync(kFull, my_e - ibase);
+    const bool staged = icnt <= kIdxCap;
+    if (staged)
+        for (int t = lane; t < icnt; t += 32) iw[t] = __ldg(indices + ibase + t);
+    __syncthreads();                                     // halo_count = 0 visible; tiles + index slices staged
+    if (already_converged) return;                       // uniform across the grid
+
+    // ---------------- step 1: turn neighbour ids into gather-tile rows; out-of-patch ones get a halo slot
+    const int rs = my_s - ibase;
+    if (staged) {
+        for (int u = 0; u < my_deg; ++u) {
+            const int g = iw[rs + u];
+            const int rel = g - tile_base;
+            int code = rel;
+            if ((unsigned)rel >= (unsigned)TILE) {
+                const int slot = atomicAdd(&halo_count, 1);
+                if (slot < HCAP) { halo_src[slot] = g; code = TILE + slot; }
+                else code = -(g + 1);                    // no slot left: that row is read from global (slow path)
+            }
+            iw[rs + u] = code;
+        }
+    }
+    // own beta_old row -> registers (fp32), thread per spot
+    float2 b2[KP / 2];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+        const float4 b4 = ld4(c_tile + L::at(wrow + lane, q));
+        b2[2 * q] = make_float2(b4.x, b4.y);
+        b2[2 * q + 1] = make_float2(b4.z, b4.w);
+    }
+    __syncwarp();
+    // the warp's fp32 rows are free again: H rows stream into them asynchronously (LDGSTS, no registers)
+    // while the halo is fetched and the neighbour sums are formed
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        const int idx = lane + 32 * i;
+        const int lr = idx / Q, q = idx - lr * Q;
+        const int p = tile_base + wrow + lr;
+        if (p < n_rows) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(c_tile + L::at(wrow + lr, q));
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(h + (size_t)p * KP + 4 * q));
+        } else {
+            st4(c_tile + L::at(wrow + lr, q), make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+    }
+    asm volatile("cp.async.commit_group;");
+    __syncthreads();                                     // halo list complete
+    // halo rows: fetched once per CTA, coalesced (Q lanes per 128-byte row), converted to fp16
+    {
+        const int n_halo = min(halo_count, HCAP);
+        for (int idx = threadIdx.x; idx < n_halo * Q; idx += TILE) {
+            const int slot = idx / Q, q = idx - slot * Q;
+            const float4 bb = ld4(beta_in + (size_t)halo_src[slot] * KP + 4 * q);
+            const __half2 lo = __floats2half2_rn(bb.x, bb.y), hi = __floats2half2_rn(bb.z, bb.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t *>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t *>(&hi);
+            *reinterpret_cast<uint2 *>(g_tile + (TILE + slot) * GROW + 2 * q) = pk;
+        }
+    }
+    __syncthreads();                                     // halo rows visible
+
+    // ---------------- step 2: neighbour sums from the fp16 gather tile, one spot per lane
+    __half2 acc[KP / 2];
+    {
+#pragma unroll
+        for (int i = 0; i < KP / 2; ++i) acc[i] = __floats2half2_rn(0.f, 0.f);
+        const int own = wrow + lane;
+        const int maxdeg = __reduce_max_sync(kFull, my_deg);
+#pragma unroll 1
+        for (int u = 0; u < maxdeg; ++u) {
+            const bool has = u < my_deg;
+            int code = own;
+            if (has) code = staged ? iw[rs + u] : -(__ldg(indices + my_s + u) + 1);
+            if (__any_sync(kFull, code < 0)) {           // rare: halo overflow / unstaged list -> fp32 row from global
+                if (code < 0) {
+                    const float *src = beta_in + (size_t)(-code - 1) * KP;
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        const float4 v = ld4(src + 4 * q);
+                        acc[2 * q] = __hadd2(acc[2 * q], __floats2half2_rn(v.x, v.y));
+                        acc[2 * q + 1] = __hadd2(acc[2 * q + 1], __floats2half2_rn(v.z, v.w));
+                    }
+                }
+            }
+            // lanes without a (shared-memory) neighbour this round re-read their own row with weight 0
+            const bool use = has && code >= 0;
+            const __half2 m = use ? __floats2half2_rn(1.f, 1.f) : __floats2half2_rn(0.f, 0.f);
+            const uint4 *row = reinterpret_cast<const uint4 *>(g_tile + (use ? code : own) * GROW);
+#pragma unroll
+            for (int q = 0; q < GQ; ++q) {
+                const uint4 w = row[q];
+                acc[4 * q] = __hfma2(*reinterpret_cast<const __half2 *>(&w.x), m, acc[4 * q]);
+                acc[4 * q + 1] = __hfma2(*reinterpret_cast<const __half2 *>(&w.y), m, acc[4 * q + 1]);
+                acc[4 * q + 2] = __hfma2(*reinterpret_cast<const __half2 *>(&w.z), m, acc[4 * q + 2]);
+                acc[4 * q + 3] = __hfma2(*reinterpret_cast<const __half2 *>(&w.w), m, acc[4 * q + 3]);
+            }
+        }
+    }
+    asm volatile("cp.async.wait_all;");
+    __syncwarp();                                        // the warp's H rows have landed in its fp32 tile rows
+
+    // ---------------- step 3: cyclic coordinate descent, direct form on packed FFMA2 (see bcd_sweep_kernel)
+    float dmax = 0.f, amax = 0.f;
+    {
+        const int trow = wrow + lane;
+        const float lam_deg = lam * (float)my_deg;
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const float4 c4 = ld4(c_tile + L::at(trow, q));
+            const float2 s01 = __half22float2(acc[2 * q]), s23 = __half22float2(acc[2 * q + 1]);
+            const float4 ns4 = make_float4(s01.x, s01.y, s23.x, s23.y);
+            float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int k = 4 * q + j;
+                if (k >= KP - 3 && k >= n_types) continue;
+                float2 a0 = make_float2(fmaf(lam, elem(ns4, j), elem(c4, j)), 0.f), a1 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int jj = 0; jj < KP / 2; ++jj) {
+                    const float2 g = make_float2(G.g[k * KP + 2 * jj], G.g[k * KP + 2 * jj + 1]);
+                    if (jj & 1) ffma2(a1, g, b2[jj]); else ffma2(a0, g, b2[jj]);
+                }
+                const float part = (a0.x + a0.y) + (a1.x + a1.y);
+                const float old = (k & 1) ? b2[k / 2].y : b2[k / 2].x;
+                const float den = G.diag[k] + lam_deg;
+                const float nv = den > 1e-10f ? fmaxf(0.f, __fdividef(part - rho, den)) : 0.f;
+                dmax = fmaxf(dmax, fabsf(nv - old));
+                amax = fmaxf(amax, fabsf(old));
+                if (k & 1) b2[k / 2].y = nv; else b2[k / 2].x = nv;
+                set_elem(n4, j, nv);
+            }
+            st4(c_tile + L::at(trow, q), n4);
+        }
+        if (my_row >= n_rows) { dmax = 0.f; amax = 0.f; }
+    }
+    __syncwarp();
+
+    // ---------------- step 4: stream the warp's new rows out
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        const int idx = lane + 32 * i;
+        const int lr = idx / Q, q = idx - lr * Q;
+        const int p = tile_base + wrow + lr;
+        if (p < n_rows) st4(beta_out + (size_t)p * KP + 4 * q, ld4(c_tile + L::at(wrow + lr, q)));
+    }
+
     const unsigned wd = __reduce_max_sync(kFull, __float_as_uint(dmax));
     const unsigned wa = __reduce_max_sync(kFull, __float_as_uint(amax));
     if (lane == 0) { red[0][warp] = wd; red[1][warp] = wa; }
@@ -544,11 +775,24 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
         FDB_LAUNCH_CHECK("bcd_sweep_kernel");
         return FDB_OK;
     };
+    if constexpr (KP <= 32 && KP % 8 == 0) {
+        if (variant == 0 || variant == 4) {               // halo-staged fp16 gather tile (default)
+            constexpr int NWH = 8, TILE = NWH * 32;
+            const size_t smem = (size_t)TILE * TileLayout<KP>::S * 4 + (size_t)2 * TILE * (KP / 2) * 4 +
+                                (size_t)NWH * kIdxCap * 4 + (size_t)TILE * 4;
+            auto kern = bcd_sweep_h_kernel<KP, NWH>;
+            FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<(int)ceil_div(n_rows, TILE), TILE, smem, st>>>(h, G, beta_in, beta_out, indptr, indices, (int)n_rows,
+                                                                 n_types, lam, rho, tol, finalize, state);
+            FDB_LAUNCH_CHECK("bcd_sweep_h_kernel");
+            return FDB_OK;
+        }
+    }
     if constexpr (KP <= 32) {
         if (variant == 1) return go(bcd_sweep_kernel<KP, 4, 1>, 4);
         if (variant == 2) return go(bcd_sweep_kernel<KP, 8, 2>, 8);
         if (variant == 3) return go(bcd_sweep_kernel<KP, 4, 2>, 4);
-        return go(bcd_sweep_kernel<KP, 8, 1>, 8);
+        return go(bcd_sweep_kernel<KP, 8, 1>, 8);        // variant 5 (or Kp % 8 != 0): fp32 gather, no halo staging
     } else {
         return go(bcd_sweep_kernel<KP, 4, 1>, 4);
     }

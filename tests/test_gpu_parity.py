@@ -128,23 +128,29 @@ def test_fused_sketch_ragged_vs_oracle(fo, monkeypatch, n, G, K, d, density, fra
     assert np.all(path.h.cpu().numpy()[:, K:] == 0)
 
 
-def test_sweep_kernel_variants_agree(monkeypatch):
-    """tile-cached sweep (default) == warp-specialised persistent sweep (FDB_SWEEP_WS), bit for bit"""
-    import subprocess, sys, os
+def test_sweep_kernel_variants_agree():
+    """The fp32 sweep kernels (tile-cached FDB_SWEEP_VARIANT=5, warp-specialised FDB_SWEEP_WS) agree bit for bit;
+    the production kernel (fp16 gather tile for the neighbour sum only) stays within 1e-5 of them."""
+    import subprocess, sys, os, json
     from conftest import ROOT
-    code = ("import numpy as np, hashlib, sys; sys.path.insert(0, %r);"
+    code = ("import numpy as np, json, sys; sys.path.insert(0, %r);"
             "from flashdeconv_b200.solver import bcd_solve; from flashdeconv_b200.graph import build_knn_graph;"
             "rng = np.random.default_rng(7); n, K, d = 5000, 30, 64;"
             "Xs = rng.standard_normal((K, d)) + 0.3; Ys = (rng.random((n, K)) * (rng.random((n, K)) < 0.3)) @ Xs;"
             "A = build_knn_graph(rng.random((n, 2)), k=6);"
             "b, info = bcd_solve(Ys, Xs, A, lambda_=1.0, rho=0.01, max_iter=20, tol=1e-12);"
-            "print(hashlib.sha256(b.tobytes()).hexdigest(), info['n_iterations'])" % ROOT)
-    outs = []
-    for env_extra in ({}, {"FDB_SWEEP_WS": "1"}):
-        env = dict(os.environ, **env_extra)
-        outs.append(subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300))
-    assert outs[0].returncode == 0 and outs[1].returncode == 0, outs[0].stderr + outs[1].stderr
-    assert outs[0].stdout.strip() == outs[1].stdout.strip() and outs[0].stdout.split()[1] == "20"
+            "np.save(sys.argv[1], b); print(info['n_iterations'])" % ROOT)
+    res = {}
+    for tag, env_extra in (("half", {}), ("tile32", {"FDB_SWEEP_VARIANT": "5"}), ("ws", {"FDB_SWEEP_WS": "1"})):
+        path = os.path.join(ROOT, "gpurun_out", f"variant_{tag}_{os.getpid()}.npy")
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        out = subprocess.run([sys.executable, "-c", code, path], capture_output=True, text=True,
+                             env=dict(os.environ, **env_extra), timeout=300)
+        assert out.returncode == 0 and out.stdout.split()[-1] == "20", out.stdout + out.stderr
+        res[tag] = np.load(path)
+        os.remove(path)
+    assert np.array_equal(res["tile32"], res["ws"])
+    assert np.max(np.abs(res["half"] - res["tile32"])) <= 1e-5 * max(1.0, np.abs(res["tile32"]).max())
 
 
 def test_projection_is_linear():
