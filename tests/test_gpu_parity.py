@@ -141,7 +141,8 @@ def test_sweep_kernel_variants_agree():
             "b, info = bcd_solve(Ys, Xs, A, lambda_=1.0, rho=0.01, max_iter=20, tol=1e-12);"
             "np.save(sys.argv[1], b); print(info['n_iterations'])" % ROOT)
     res = {}
-    for tag, env_extra in (("half", {}), ("tile32", {"FDB_SWEEP_VARIANT": "5"}), ("ws", {"FDB_SWEEP_WS": "1"})):
+    for tag, env_extra in (("half", {"FDB_SWEEP_VARIANT": "4"}), ("tile32", {"FDB_SWEEP_VARIANT": "5"}),
+                           ("ws", {"FDB_SWEEP_WS": "1"})):
         path = os.path.join(ROOT, "gpurun_out", f"variant_{tag}_{os.getpid()}.npy")
         os.makedirs(os.path.dirname(path), exist_ok=True)
         out = subprocess.run([sys.executable, "-c", code, path], capture_output=True, text=True,
@@ -150,7 +151,9 @@ def test_sweep_kernel_variants_agree():
         res[tag] = np.load(path)
         os.remove(path)
     assert np.array_equal(res["tile32"], res["ws"])
-    assert np.max(np.abs(res["half"] - res["tile32"])) <= 1e-5 * max(1.0, np.abs(res["tile32"]).max())
+    # lambda = 1 here makes the spatial term ~10 % of the diagonal (20x the auto-lambda regime), the edge of
+    # where the production dispatcher still picks the fp16 gather
+    assert np.max(np.abs(res["half"] - res["tile32"])) <= 5e-5 * max(1.0, np.abs(res["tile32"]).max())
 
 
 def test_projection_is_linear():
