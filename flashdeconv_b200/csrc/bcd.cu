@@ -790,7 +790,7 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
         float mean_diag = 0.f;
         for (int k = 0; k < n_types; ++k) mean_diag += host_gram[k * n_types + k];
         mean_diag /= (float)n_types;
-        const bool weak_coupling = lam * 8.f <= 0.1f * mean_diag;
+        const bool weak_coupling = lam * 8.f <= 0.02f * mean_diag;
         if ((variant == 0 && weak_coupling) || variant == 4) {   // halo-staged fp16 gather tile (default)
             constexpr int NWH = 8, TILE = NWH * 32;
             const size_t smem = (size_t)TILE * TileLayout<KP>::S * 4 + (size_t)2 * TILE * (KP / 2) * 4 +
@@ -880,10 +880,18 @@ objective_kernel(const float *__restrict__ beta, const float *__restrict__ h, co
         }
         const int s = indptr[p], e = indptr[p + 1];
         float n0 = 0.f, n1 = 0.f;
-        for (int j = s; j < e; ++j) {
-            const int64_t nb = indices[j];
-            if (on0) n0 += beta[nb * kp + lane];
-            if (on1) n1 += beta[nb * kp + 32 + lane];
+        for (int j0 = s; j0 < e; j0 += 8) {                 // 8 independent row reads in flight
+            int nb[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) nb[u] = j0 + u < e ? __ldg(indices + j0 + u) : -1;
+            float v0[8], v1[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                v0[u] = (on0 && nb[u] >= 0) ? beta[(int64_t)nb[u] * kp + lane] : 0.f;
+                v1[u] = (on1 && nb[u] >= 0) ? beta[(int64_t)nb[u] * kp + 32 + lane] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { n0 += v0[u]; n1 += v1[u]; }
         }
         const float deg = (float)(e - s);
         cross += (double)(b0 * h0) + (double)(b1 * h1);

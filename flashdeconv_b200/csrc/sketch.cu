@@ -358,6 +358,225 @@ sketch_contract_v2_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
 }
 
 // ------------------------------------------------------------------------------------
+// fused form, v3 (production when the number of selected genes is known): v2 plus
+//   * NO global table lookups while streaming: a u16 gene -> slot table and a slot -> (bucket, weight)
+//     table are built in shared memory by each CTA (block scan over the gene axis), so the dependent
+//     index -> weight L2 round trip of v2 is gone;
+//   * cross-row software pipelining: the first 512 entries of the NEXT row are loaded into registers
+//     before the lane-parallel AXPY of the current row runs, so each warp always has 16 coalesced
+//     128-byte loads in flight (16 warps/SM x 16 x 128 B x 2 arrays = 64 KB per SM).
+// ------------------------------------------------------------------------------------
+constexpr int kPrefetch = 16;       // register-prefetched chunks of 32 entries (first 512 entries of a row)
+
+template <typename IndPtr, int NK>
+__global__ void __launch_bounds__(512, 1)
+sketch_contract_v3_kernel(const IndPtr *__restrict__ indptr, const int32_t *__restrict__ indices,
+                          const float *__restrict__ counts, int64_t n_spots, int n_genes, int n_selected,
+                          const int32_t *__restrict__ gene_bucket, const float *__restrict__ gene_weight,
+                          int d, const float *__restrict__ x_sketch_t, int kp,
+                          const int32_t *__restrict__ row_map, const int32_t *__restrict__ row_ids,
+                          float *__restrict__ h, float *__restrict__ ysq)
+{
+    constexpr int XR = NK * 32 + 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int warps_per_cta = blockDim.x >> 5;
+    const int per_warp_floats = d + kListCap + kListCap / 2;
+    float *xs = reinterpret_cast<float *>(smem_raw);                                    // d x XR
+    int2 *slot_bw = reinterpret_cast<int2 *>(xs + (size_t)d * XR);                      // n_selected (bucket, weight bits)
+    float *warp_base = reinterpret_cast<float *>(slot_bw + ((n_selected + 1) & ~1)) + (size_t)warp * per_warp_floats;
+    float *acc = warp_base;                                                             // d
+    float *list_v = acc + d;                                                            // kListCap
+    unsigned short *list_s = reinterpret_cast<unsigned short *>(list_v + kListCap);     // kListCap (u16 slots)
+    unsigned short *gslot = reinterpret_cast<unsigned short *>(
+        reinterpret_cast<float *>(slot_bw + ((n_selected + 1) & ~1)) + (size_t)warps_per_cta * per_warp_floats);
+    __shared__ int scan_warp[32];
+
+    for (int i = threadIdx.x; i < d * XR; i += blockDim.x) {
+        const int r = i / XR, c = i - r * XR;
+        xs[i] = c < kp ? __ldg(x_sketch_t + (size_t)r * kp + c) : 0.f;
+    }
+    for (int c = lane; c < d; c += 32) acc[c] = 0.f;
+    {   // gene -> slot (rank among selected genes): block-wide exclusive scan over contiguous gene chunks
+        const int per = (n_genes + (int)blockDim.x - 1) / (int)blockDim.x;
+        const int g0 = min((int)threadIdx.x * per, n_genes), g1 = min(g0 + per, n_genes);
+        int mine = 0;
+        for (int g = g0; g < g1; ++g) mine += __ldg(gene_bucket + g) >= 0;
+        int inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFull, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) scan_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = lane < warps_per_cta ? scan_warp[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(kFull, w, o);
+                if (lane >= o) w += t;
+            }
+            scan_warp[lane] = w;
+        }
+        __syncthreads();
+        int slot = (warp ? scan_warp[warp - 1] : 0) + inc - mine;
+        for (int g = g0; g < g1; ++g) {
+            const int b = __ldg(gene_bucket + g);
+            unsigned short code = 0xFFFF;
+            if (b >= 0 && slot < n_selected && slot < 0xFFFF) {
+                slot_bw[slot] = make_int2(b, __float_as_int(__ldg(gene_weight + g)));
+                code = (unsigned short)slot;
+                ++slot;
+            }
+            gslot[g] = code;
+        }
+    }
+    __syncthreads();
+
+    unsigned lt_mask;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
+    const int64_t stride = (int64_t)gridDim.x * warps_per_cta;
+
+    // lane-parallel AXPY over list[0, n) with the row's scale
+    float hv[NK * 32];
+    auto flush = [&](int n, float scale) {
+        for (int t0 = 0; t0 < n; t0 += 32) {
+            const int t = t0 + lane;
+            if (t < n) {
+                const int2 bw = slot_bw[list_s[t]];
+                const float c = log1pf(list_v[t] * scale) * __int_as_float(bw.y);
+                atomicAdd(acc + bw.x, c);
+                const float4 *xr = reinterpret_cast<const float4 *>(xs + bw.x * XR);
+#pragma unroll
+                for (int q = 0; q < NK * 8; ++q) {
+                    const float4 x = xr[q];
+                    hv[4 * q] = fmaf(c, x.x, hv[4 * q]);
+                    hv[4 * q + 1] = fmaf(c, x.y, hv[4 * q + 1]);
+                    hv[4 * q + 2] = fmaf(c, x.z, hv[4 * q + 2]);
+                    hv[4 * q + 3] = fmaf(c, x.w, hv[4 * q + 3]);
+                }
+            }
+        }
+    };
+    // one chunk of 32 entries: look the slot up, add to the library size, append selected entries to the list
+    auto take = [&](int g, float v, int &cnt, float &lib, float scale, bool flush_when_full) {
+        const unsigned sl = g >= 0 ? gslot[g] : 0xFFFFu;
+        const bool sel = sl != 0xFFFFu;
+        const unsigned m = __ballot_sync(kFull, sel);
+        if (flush_when_full && cnt + 32 > kListCap) {
+            __syncwarp();
+            flush(cnt, scale);
+            __syncwarp();
+            cnt = 0;
+        }
+        if (sel) {
+            lib += v;
+            const int pos = cnt + __popc(m & lt_mask);
+            if (pos < kListCap) {
+                list_v[pos] = v;
+                list_s[pos] = (unsigned short)sl;
+            }
+        }
+        cnt += __popc(m);
+    };
+    auto row_of = [&](int64_t it) { return row_ids ? (int64_t)__ldg(row_ids + it) : it; };
+
+    int64_t it = (int64_t)blockIdx.x * warps_per_cta + warp;
+    int pg[kPrefetch];
+    float pv[kPrefetch];
+    int64_t s = 0, e = 0, row = 0;
+    if (it < n_spots) {
+        row = row_of(it);
+        s = load_ptr(indptr, row);
+        e = load_ptr(indptr, row + 1);
+    }
+#pragma unroll
+    for (int u = 0; u < kPrefetch; ++u) {
+        const int64_t j = s + 32 * u + lane;
+        pg[u] = j < e ? ld_stream(indices + j) : -1;
+        pv[u] = j < e ? ld_stream(counts + j) : 0.f;
+    }
+    while (it < n_spots) {
+        const int64_t it_next = it + stride;
+        int64_t s2 = 0, e2 = 0, row2 = 0;
+        if (it_next < n_spots) {
+            row2 = row_of(it_next);
+            s2 = load_ptr(indptr, row2);
+            e2 = load_ptr(indptr, row2 + 1);
+        }
+#pragma unroll
+        for (int i = 0; i < NK * 32; ++i) hv[i] = 0.f;
+        int cnt = 0;
+        float lib = 0.f;
+#pragma unroll
+        for (int u = 0; u < kPrefetch; ++u) {
+            if (s + 32 * u >= e) break;                                   // warp-uniform
+            take(pg[u], pv[u], cnt, lib, 0.f, false);
+        }
+        for (int64_t j0 = s + 32 * kPrefetch; j0 < e; j0 += 128) {        // long rows: the rest, 4 chunks at a time
+            int g[4];
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t j = j0 + 32 * u + lane;
+                g[u] = j < e ? ld_stream(indices + j) : -1;
+                v[u] = j < e ? ld_stream(counts + j) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (j0 + 32 * u >= e) break;
+                take(g[u], v[u], cnt, lib, 0.f, false);
+            }
+        }
+        lib = warp_sum(lib);
+        if (lib == 0.f) lib = 1.f;
+        const float scale = 1e4f / lib;
+        const bool overflow = cnt > kListCap;
+        // next row's first 512 entries start streaming now and land while this row's AXPY runs
+        const int64_t cs = s, ce = e;
+#pragma unroll
+        for (int u = 0; u < kPrefetch; ++u) {
+            const int64_t j = s2 + 32 * u + lane;
+            pg[u] = j < e2 ? ld_stream(indices + j) : -1;
+            pv[u] = j < e2 ? ld_stream(counts + j) : 0.f;
+        }
+        __syncwarp();
+        if (!overflow) {
+            flush(cnt, scale);
+        } else {                                   // rare: more selected entries than the list holds -> re-stream
+            int c2 = 0;
+            float dummy = 0.f;
+            for (int64_t j0 = cs; j0 < ce; j0 += 32) {
+                const int64_t j = j0 + lane;
+                const int g = j < ce ? ld_stream(indices + j) : -1;
+                const float v = j < ce ? ld_stream(counts + j) : 0.f;
+                take(g, v, c2, dummy, scale, true);
+            }
+            __syncwarp();
+            flush(c2, scale);
+        }
+        __syncwarp();
+        lane_reduce_transpose<NK>(hv, lane);
+        float sq = 0.f;
+        for (int c = lane * 4; c < d; c += 128) {
+            const float4 a = *reinterpret_cast<float4 *>(acc + c);
+            *reinterpret_cast<float4 *>(acc + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+            sq = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, sq))));
+        }
+        sq = warp_sum(sq);
+        const int64_t orow = row_map ? (int64_t)__ldg(row_map + row) : it;
+        float *out = h + orow * kp;
+        if (lane < kp) out[lane] = hv[0];
+        if (NK == 2 && 32 + lane < kp) out[32 + lane] = hv[1];
+        if (lane == 0) ysq[orow] = sq;
+        __syncwarp();
+        it = it_next; s = s2; e = e2; row = row2;
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // unfused contraction (API / parity form): H = Y_s X_s^T, ysq = rowwise ||y_s||^2
 // one warp per spot, X_s staged in shared memory
 // ------------------------------------------------------------------------------------
@@ -497,11 +716,30 @@ extern "C" __attribute__((visibility("default"))) int fdb_contract(const float *
 
 template <typename IndPtr, int NK>
 static int launch_fused(const void *indptr, const int32_t *indices, const float *counts,
-                        int64_t n_spots, int n_genes, const int32_t *gene_bucket, const float *gene_weight,
-                        int d, const float *x_sketch_t, int kp, const int32_t *row_map, const int32_t *row_ids, float *h,
-                        float *ysq, cudaStream_t st)
+                        int64_t n_spots, int n_genes, int n_selected, const int32_t *gene_bucket,
+                        const float *gene_weight, int d, const float *x_sketch_t, int kp, const int32_t *row_map,
+                        const int32_t *row_ids, float *h, float *ysq, cudaStream_t st)
 {
-    // preferred: v2 (tables + compaction lists in shared memory), one 16/12/8/4-warp CTA per SM
+    // preferred: v3 (gene->slot and slot->(bucket, weight) tables + compaction lists in shared memory)
+    if (n_selected >= 0 && n_selected < 0xFFFF && getenv("FDB_SKETCH_V1") == nullptr && getenv("FDB_SKETCH_V2") == nullptr) {
+        constexpr int XR = NK * 32 + 4;
+        const size_t fixed = (size_t)d * XR * 4 + (size_t)((n_selected + 1) & ~1) * 8 + (size_t)n_genes * 2 + 16;
+        const size_t per_warp = ((size_t)d + kListCap + kListCap / 2) * 4;
+        int warps = 0;
+        for (int w : {16, 12, 8, 4})
+            if (fixed + w * per_warp <= 227 * 1024) { warps = w; break; }
+        if (warps) {
+            const size_t smem = fixed + warps * per_warp;
+            auto kern = sketch_contract_v3_kernel<IndPtr, NK>;
+            FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int grid = pick_grid(n_spots, warps, 1);
+            kern<<<grid, warps * 32, smem, st>>>((const IndPtr *)indptr, indices, counts, n_spots, n_genes, n_selected,
+                                                 gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq);
+            FDB_LAUNCH_CHECK("sketch_contract_v3_kernel");
+            return FDB_OK;
+        }
+    }
+    // next: v2 (bucket table + compaction lists in shared memory, weights from L2)
     {
         constexpr int XR = NK * 32 + 4;
         const size_t fixed = (size_t)d * XR * 4 + (size_t)n_genes * 2 + 16;
@@ -549,7 +787,7 @@ extern "C" __attribute__((visibility("default"))) int fdb_sketch_contract_csr(co
                                        const float *counts, int64_t n_spots, int32_t n_genes,
                                        const int32_t *gene_bucket, const float *gene_weight, int32_t d,
                                        const float *x_sketch_t, int32_t n_types, const int32_t *row_map,
-                                       const int32_t *row_ids, float *h, float *ysq, void *stream)
+                                       const int32_t *row_ids, int32_t n_selected, float *h, float *ysq, void *stream)
 {
     FDB_REQUIRE(n_spots >= 0 && n_genes >= 0, "negative shape");
     FDB_REQUIRE(d > 0 && d % 4 == 0, "sketch_dim must be a positive multiple of 4, got %d", d);
@@ -560,11 +798,11 @@ extern "C" __attribute__((visibility("default"))) int fdb_sketch_contract_csr(co
     cudaStream_t st = (cudaStream_t)stream;
     if (kp <= 32)
         return indptr_is_int64
-                   ? launch_fused<int64_t, 1>(indptr, indices, counts, n_spots, n_genes, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, st)
-                   : launch_fused<int32_t, 1>(indptr, indices, counts, n_spots, n_genes, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, st);
+                   ? launch_fused<int64_t, 1>(indptr, indices, counts, n_spots, n_genes, n_selected, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, st)
+                   : launch_fused<int32_t, 1>(indptr, indices, counts, n_spots, n_genes, n_selected, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, st);
     return indptr_is_int64
-               ? launch_fused<int64_t, 2>(indptr, indices, counts, n_spots, n_genes, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, st)
-               : launch_fused<int32_t, 2>(indptr, indices, counts, n_spots, n_genes, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, st);
+               ? launch_fused<int64_t, 2>(indptr, indices, counts, n_spots, n_genes, n_selected, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, st)
+               : launch_fused<int32_t, 2>(indptr, indices, counts, n_spots, n_genes, n_selected, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, st);
 }
 
 extern "C" __attribute__((visibility("default"))) int fdb_gene_moments_csr(const void *indptr, int indptr_is_int64, const int32_t *indices,

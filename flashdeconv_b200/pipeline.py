@@ -243,7 +243,7 @@ class DevicePath:
         check(lib.fdb_sketch_contract_csr(_ptr(c.indptr), int(c.indptr.dtype == self.torch.int64), _ptr(c.indices),
                                           _ptr(c.data), c.shape[0], c.shape[1], _ptr(self.gene_bucket),
                                           _ptr(self.gene_weight), tb.d, _ptr(self.x_sketch_t), self.K,
-                                          _ptr(row_map), _ptr(None), _ptr(self.h), _ptr(self.ysq),
+                                          _ptr(row_map), _ptr(None), int(len(tb.bucket)), _ptr(self.h), _ptr(self.ysq),
                                           _stream(self.torch)),
               "sketch_contract_csr")
 

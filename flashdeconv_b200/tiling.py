@@ -187,7 +187,7 @@ class TiledPath:
         self.check(self.lib.fdb_sketch_contract_csr(
             self.pl._ptr(c.indptr), int(c.indptr.dtype == self.torch.int64), self.pl._ptr(c.indices),
             self.pl._ptr(c.data), p.n_own, c.shape[1], self.pl._ptr(self.gene_bucket), self.pl._ptr(self.gene_weight),
-            tb.d, self.pl._ptr(self.x_sketch_t), self.K, self.pl._ptr(None), self.pl._ptr(row_ids),
+            tb.d, self.pl._ptr(self.x_sketch_t), self.K, self.pl._ptr(None), self.pl._ptr(row_ids), int(len(tb.bucket)),
             self.pl._ptr(self.h), self.pl._ptr(self.ysq), self._stream()), "sketch_contract_csr")
 
     def lambda_auto(self, alpha=0.005) -> float:

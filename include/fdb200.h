@@ -78,12 +78,14 @@ int fdb_contract(const float *y_sketch, const float *x_sketch, int64_t n_spots, 
  * for i in [0, n_spots), where row(i) = row_ids ? row_ids[i] : i is the CSR row processed and
  * out(i) = row_map ? row_map[row(i)] : i.  row_map places results in tile order (single GPU);
  * row_ids selects the rows of one spatial tile (multi-GPU: row_ids = order[lo:hi], out = i).
- * x_sketch_t is the TRANSPOSED sketched reference, d x Kp row-major (padding columns zero). */
+ * x_sketch_t is the TRANSPOSED sketched reference, d x Kp row-major (padding columns zero).
+ * n_selected = number of genes with gene_bucket >= 0 (sizes the shared-memory tables of the fastest
+ * kernel), or -1 if unknown (a slower kernel that needs no such count is used). */
 int fdb_sketch_contract_csr(const void *indptr, int indptr_is_int64, const int32_t *indices,
                             const float *counts, int64_t n_spots, int32_t n_genes,
                             const int32_t *gene_bucket, const float *gene_weight, int32_t d,
                             const float *x_sketch_t, int32_t n_types, const int32_t *row_map,
-                            const int32_t *row_ids, float *h, float *ysq, void *stream);
+                            const int32_t *row_ids, int32_t n_selected, float *h, float *ysq, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * (a5) spatial graph.  Replaces build_knn_graph (utils/graph.py:25-83), build_radius_graph
