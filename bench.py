@@ -102,14 +102,8 @@ class ClockSampler:
 
 def select_genes_device(csr, X, n_spots):
     """Step 1 (not part of the metric): HVG moments on the device, ranking + SVD on the host."""
-    from flashdeconv_b200 import genes, pipeline
-    sums, sq = pipeline.gene_moments(csr)
-    mean = sums / n_spots
-    var = np.maximum(n_spots / (n_spots - 1) * (sq / n_spots - mean ** 2), 0)
-    hvg = genes._rank_hvg(mean, var, SOLVER["n_hvg"], 0.0125, 3.0, 0.5)
-    markers, _ = genes.select_markers(X, SOLVER["n_markers"])
-    gene_idx = np.union1d(hvg, markers).astype(np.intp)
-    return gene_idx, genes.compute_leverage_scores(X[:, gene_idx])
+    from flashdeconv_b200 import genes
+    return genes.select_informative_genes_device(csr, X, SOLVER["n_hvg"], SOLVER["n_markers"])
 
 
 def cpu_sample(data, cfg, gene_idx, leverage, n_sample):

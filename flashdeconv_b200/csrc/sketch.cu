@@ -621,17 +621,19 @@ gene_moments_kernel(const IndPtr *__restrict__ indptr, const int32_t *__restrict
                     const float *__restrict__ counts, int64_t n_spots, double *__restrict__ sums,
                     double *__restrict__ sumsq)
 {
+    // float64 throughout: the ranking built from these moments must reproduce the reference's gene
+    // selection exactly, so only the summation order may differ from numpy (utils/genes.py:57-75)
     const int lane = threadIdx.x & 31;
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t row = warp_global; row < n_spots; row += n_warps) {
         const int64_t s = load_ptr(indptr, row), e = load_ptr(indptr, row + 1);
-        float lib = 0.f;
-        for (int64_t j = s + lane; j < e; j += 32) lib += __ldg(counts + j);
+        double lib = 0.0;
+        for (int64_t j = s + lane; j < e; j += 32) lib += (double)__ldg(counts + j);
         lib = warp_sum(lib);
-        const float scale = 1e4f / fmaxf(lib, 1.f);
+        const double scale = 10000.0 / fmax(lib, 1.0);
         for (int64_t j = s + lane; j < e; j += 32) {
-            const double z = (double)log1pf(__ldg(counts + j) * scale);
+            const double z = log1p(scale * (double)__ldg(counts + j));
             const int g = ld_stream(indices + j);
             atomicAdd(sums + g, z);
             atomicAdd(sumsq + g, z * z);

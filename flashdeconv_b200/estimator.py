@@ -95,16 +95,18 @@ class FlashDeconv:
         self.n_cell_types_ = X.shape[0]
         self.cell_type_names_ = cell_type_names
 
+        pipeline._native.require_cuda()
         say("Step 1: Selecting informative genes...")
-        gene_idx, leverage = genes.select_informative_genes(Y, X, n_hvg=self.n_hvg,
-                                                            n_markers_per_type=self.n_markers_per_type)
+        # counts go to the device once; the O(nnz) moment pass of the HVG selection runs there too
+        # (SURVEY 8 f1), the G-sized ranking and the K x G_sel SVD stay on the host
+        csr = pipeline.csr_to_device(Y)
+        gene_idx, leverage = genes.select_informative_genes_device(csr, np.asarray(X), n_hvg=self.n_hvg,
+                                                                   n_markers_per_type=self.n_markers_per_type)
         self.gene_idx_ = gene_idx
         say(f"  Selected {len(gene_idx)} genes (HVG + markers)")
-
-        torch = pipeline._native.require_cuda()
         say(f"Step 2-3: log-CPM + sketching to {self.sketch_dim} dimensions (fused, on device)...")
         say("Step 4-6: spatial graph, lambda, block coordinate descent...")
-        res = pipeline.deconvolve_path(Y, X, coords, gene_idx, leverage, sketch_dim=self.sketch_dim,
+        res = pipeline.deconvolve_path(csr, X, coords, gene_idx, leverage, sketch_dim=self.sketch_dim,
                                        lambda_spatial=self.lambda_spatial, rho_sparsity=self.rho_sparsity,
                                        spatial_method=self.spatial_method, k_neighbors=self.k_neighbors,
                                        radius=self.radius, max_iter=self.max_iter, tol=self.tol,

@@ -110,3 +110,23 @@ def select_informative_genes(Y, X: np.ndarray, n_hvg: int = 2000, n_markers_per_
     if gene_idx.size == 0:
         raise ValueError("No genes selected. Increase n_hvg or n_markers_per_type.")
     return gene_idx, compute_leverage_scores(X[:, gene_idx])
+
+
+def select_informative_genes_device(csr, X: np.ndarray, n_hvg: int = 2000, n_markers_per_type: int = 50):
+    """Same selection as `select_informative_genes`, with the O(nnz) moment pass of select_hvg
+    (utils/genes.py:52-83) run on the GPU over a `pipeline.DeviceCSR` (float64 accumulation); the G-sized
+    binning / ranking, the marker pick and the K x G_sel SVD stay on the host."""
+    from . import pipeline
+    n = csr.shape[0]
+    sums, sumsq = pipeline.gene_moments(csr)
+    mean = sums / n
+    if n >= 2:
+        var = np.maximum(n / (n - 1) * (sumsq / n - mean ** 2), 0)
+    else:
+        var = np.zeros_like(mean)
+    hvg = _rank_hvg(mean, var, n_hvg, 0.0125, 3.0, 0.5)
+    markers, _ = select_markers(X, n_markers=n_markers_per_type)
+    gene_idx = np.union1d(hvg, markers).astype(np.intp)
+    if gene_idx.size == 0:
+        raise ValueError("No genes selected. Increase n_hvg or n_markers_per_type.")
+    return gene_idx, compute_leverage_scores(X[:, gene_idx])

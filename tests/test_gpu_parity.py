@@ -390,3 +390,23 @@ def test_tiled_path_two_ranks_equals_device_path():
     out = _run_tiled(2)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "OK" in out.stdout
+
+
+# ---------------------------------------------------------------- f1: gene moments on the device
+def test_device_gene_selection_equals_host_selection():
+    """float64 moment pass on the GPU -> the very same HVG/marker set as the host (= reference) code"""
+    from flashdeconv_b200 import genes, pipeline
+    from flashdeconv_b200.synth import make_dataset
+    ds = make_dataset(n_spots=6000, n_genes=5000, n_types=8, depth=600.0, seed=9)
+    Y = ds.Y.astype(np.float64)
+    want_idx, want_lev = genes.select_informative_genes(Y, ds.X, 2000, 50)
+    got_idx, got_lev = genes.select_informative_genes_device(pipeline.csr_to_device(ds.Y), ds.X, 2000, 50)
+    assert want_idx.size < 5000                                   # a real selection, not "all genes"
+    assert np.array_equal(got_idx, want_idx)
+    np.testing.assert_allclose(got_lev, want_lev, rtol=1e-12)
+    sums, sq = pipeline.gene_moments(pipeline.csr_to_device(ds.Y))
+    lib = np.maximum(np.asarray(Y.sum(axis=1)).ravel(), 1.0)
+    Z = sparse.diags(1e4 / lib) @ Y
+    Z.data = np.log1p(Z.data)
+    np.testing.assert_allclose(sums, np.asarray(Z.sum(axis=0)).ravel(), rtol=1e-12)
+    np.testing.assert_allclose(sq, np.asarray(Z.multiply(Z).sum(axis=0)).ravel(), rtol=1e-12)
