@@ -264,6 +264,8 @@ def main():
                   for k in ("indptr", "indices", "data", "coords")))
     d2h = int(2 * n * K * 8)
 
+    if distributed:
+        tiling.release_communicators()
     if rank != 0:
         if distributed:
             dist.destroy_process_group()

@@ -483,28 +483,35 @@ sketch_contract_v3_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
     };
     auto row_of = [&](int64_t it) { return row_ids ? (int64_t)__ldg(row_ids + it) : it; };
 
+    // 32-bit offsets inside a row (rows longer than 2^31 entries are rejected on the host)
     int64_t it = (int64_t)blockIdx.x * warps_per_cta + warp;
     int pg[kPrefetch];
     float pv[kPrefetch];
-    int64_t s = 0, e = 0, row = 0;
+    int64_t s = 0, row = 0;
+    int len = 0;
     if (it < n_spots) {
         row = row_of(it);
         s = load_ptr(indptr, row);
-        e = load_ptr(indptr, row + 1);
+        len = (int)(load_ptr(indptr, row + 1) - s);
     }
+    {
+        const int32_t *ip = indices + s;
+        const float *vp = counts + s;
 #pragma unroll
-    for (int u = 0; u < kPrefetch; ++u) {
-        const int64_t j = s + 32 * u + lane;
-        pg[u] = j < e ? ld_stream(indices + j) : -1;
-        pv[u] = j < e ? ld_stream(counts + j) : 0.f;
+        for (int u = 0; u < kPrefetch; ++u) {
+            const int j = 32 * u + lane;
+            pg[u] = j < len ? ld_stream(ip + j) : -1;
+            pv[u] = j < len ? ld_stream(vp + j) : 0.f;
+        }
     }
     while (it < n_spots) {
         const int64_t it_next = it + stride;
-        int64_t s2 = 0, e2 = 0, row2 = 0;
+        int64_t s2 = 0, row2 = 0;
+        int len2 = 0;
         if (it_next < n_spots) {
             row2 = row_of(it_next);
             s2 = load_ptr(indptr, row2);
-            e2 = load_ptr(indptr, row2 + 1);
+            len2 = (int)(load_ptr(indptr, row2 + 1) - s2);
         }
 #pragma unroll
         for (int i = 0; i < NK * 32; ++i) hv[i] = 0.f;
@@ -512,22 +519,26 @@ sketch_contract_v3_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
         float lib = 0.f;
 #pragma unroll
         for (int u = 0; u < kPrefetch; ++u) {
-            if (s + 32 * u >= e) break;                                   // warp-uniform
+            if (32 * u >= len) break;                                     // warp-uniform
             take(pg[u], pv[u], cnt, lib, 0.f, false);
         }
-        for (int64_t j0 = s + 32 * kPrefetch; j0 < e; j0 += 128) {        // long rows: the rest, 4 chunks at a time
-            int g[4];
-            float v[4];
+        {
+            const int32_t *ip = indices + s;
+            const float *vp = counts + s;
+            for (int j0 = 32 * kPrefetch; j0 < len; j0 += 128) {          // long rows: the rest, 4 chunks at a time
+                int g[4];
+                float v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int64_t j = j0 + 32 * u + lane;
-                g[u] = j < e ? ld_stream(indices + j) : -1;
-                v[u] = j < e ? ld_stream(counts + j) : 0.f;
-            }
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + 32 * u + lane;
+                    g[u] = j < len ? ld_stream(ip + j) : -1;
+                    v[u] = j < len ? ld_stream(vp + j) : 0.f;
+                }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (j0 + 32 * u >= e) break;
-                take(g[u], v[u], cnt, lib, 0.f, false);
+                for (int u = 0; u < 4; ++u) {
+                    if (j0 + 32 * u >= len) break;
+                    take(g[u], v[u], cnt, lib, 0.f, false);
+                }
             }
         }
         lib = warp_sum(lib);
@@ -535,12 +546,15 @@ sketch_contract_v3_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
         const float scale = 1e4f / lib;
         const bool overflow = cnt > kListCap;
         // next row's first 512 entries start streaming now and land while this row's AXPY runs
-        const int64_t cs = s, ce = e;
+        {
+            const int32_t *ip = indices + s2;
+            const float *vp = counts + s2;
 #pragma unroll
-        for (int u = 0; u < kPrefetch; ++u) {
-            const int64_t j = s2 + 32 * u + lane;
-            pg[u] = j < e2 ? ld_stream(indices + j) : -1;
-            pv[u] = j < e2 ? ld_stream(counts + j) : 0.f;
+            for (int u = 0; u < kPrefetch; ++u) {
+                const int j = 32 * u + lane;
+                pg[u] = j < len2 ? ld_stream(ip + j) : -1;
+                pv[u] = j < len2 ? ld_stream(vp + j) : 0.f;
+            }
         }
         __syncwarp();
         if (!overflow) {
@@ -548,10 +562,12 @@ sketch_contract_v3_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
         } else {                                   // rare: more selected entries than the list holds -> re-stream
             int c2 = 0;
             float dummy = 0.f;
-            for (int64_t j0 = cs; j0 < ce; j0 += 32) {
-                const int64_t j = j0 + lane;
-                const int g = j < ce ? ld_stream(indices + j) : -1;
-                const float v = j < ce ? ld_stream(counts + j) : 0.f;
+            const int32_t *ip = indices + s;
+            const float *vp = counts + s;
+            for (int j0 = 0; j0 < len; j0 += 32) {
+                const int j = j0 + lane;
+                const int g = j < len ? ld_stream(ip + j) : -1;
+                const float v = j < len ? ld_stream(vp + j) : 0.f;
                 take(g, v, c2, dummy, scale, true);
             }
             __syncwarp();
@@ -572,7 +588,7 @@ sketch_contract_v3_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
         if (NK == 2 && 32 + lane < kp) out[32 + lane] = hv[1];
         if (lane == 0) ysq[orow] = sq;
         __syncwarp();
-        it = it_next; s = s2; e = e2; row = row2;
+        it = it_next; s = s2; len = len2; row = row2;
     }
 }
 

@@ -26,6 +26,20 @@ from typing import Callable, List, Optional, Tuple
 import numpy as np
 
 
+_COMM_CACHE = {}
+
+
+def release_communicators():
+    """Destroy the cached native NCCL communicators (call before torch.distributed.destroy_process_group)."""
+    import torch
+    from . import _native
+    if _COMM_CACHE and torch.cuda.is_available():
+        torch.cuda.synchronize()
+    for comm in _COMM_CACHE.values():
+        _native.lib.fdb_comm_destroy(comm)
+    _COMM_CACHE.clear()
+
+
 def tile_bounds(n: int, world: int, align: int = 256) -> List[Tuple[int, int]]:
     """Contiguous position ranges, one per rank, cut at multiples of `align` (the sweep kernel's CTA tile)."""
     if world <= 0:
@@ -139,10 +153,14 @@ class TiledPath:
 
     def _native_comm(self):
         """NCCL communicator owned by libfdb200 (the solve loop issues its collectives from C).  The unique id
-        travels over the existing torch.distributed group.  FDB_TILED_TORCH=1 keeps everything in torch."""
+        travels over the existing torch.distributed group; the communicator is created once per group and
+        cached (ncclCommInitRank costs seconds).  FDB_TILED_TORCH=1 keeps everything in torch."""
         import os
         if os.environ.get("FDB_TILED_TORCH"):
             return None
+        key = id(self.group) if self.group is not None else None
+        if key in _COMM_CACHE:
+            return _COMM_CACHE[key]
         buf = C.create_string_buffer(128)
         if self.rank == 0:
             self.check(self.lib.fdb_comm_unique_id(buf), "comm_unique_id")
@@ -151,13 +169,12 @@ class TiledPath:
                                         group=self.group)
         comm = C.c_void_p()
         self.check(self.lib.fdb_comm_init(self.rank, self.world, box[0], C.byref(comm)), "comm_init")
+        _COMM_CACHE[key] = comm
         return comm
 
     def close(self):
-        if getattr(self, "comm", None):
-            self.torch.cuda.synchronize()
-            self.lib.fdb_comm_destroy(self.comm)
-            self.comm = None
+        """Kept for symmetry; the communicator is cached per group and released by `release_communicators`."""
+        self.comm = None
 
     def _stream(self):
         return self.pl._stream(self.torch)

@@ -36,6 +36,7 @@ def main():
           and abs(lam - single.lambda_used) <= 1e-12 * lam)
     halo = tp.plan.n_halo
     tp.close()
+    tiling.release_communicators()
     flags = torch.tensor([int(ok), halo], device="cuda")
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if rank == 0:
