@@ -45,7 +45,7 @@ struct SolveState {                 // mirrors the 64-byte block documented in f
 static_assert(sizeof(SolveState) == 64, "state block is 64 bytes");
 
 template <int KP>
-struct GramArg {
+struct alignas(16) GramArg {
     float g[KP * KP];               // g[k*KP+j] = -G[k][j] for j != k, 0 on the diagonal; zero padded
     float diag[KP];                 // G[k][k]
 };
@@ -61,6 +61,29 @@ __device__ __forceinline__ void ffma2(float2 &d, const float2 a, const float2 b)
     unsigned long long ud = *reinterpret_cast<unsigned long long *>(&d);
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(ud) : "l"(ua), "l"(ub));
     d = *reinterpret_cast<float2 *>(&ud);
+}
+// 64-bit register-pair forms: keeping beta pairs and accumulators as b64 values lets ptxas hold them in
+// aligned even/odd register pairs, so FFMA2 needs no MOVs to assemble its operands
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi)
+{
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void ffma2q(u64 &d, const u64 a, const u64 b)
+{
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ float rcp_fast(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 __device__ __forceinline__ float elem(const float4 &v, int j) { return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w; }
 __device__ __forceinline__ void set_elem(float4 &v, int j, float x)
@@ -362,12 +385,12 @@ bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
         }
     }
     // own beta_old row -> registers (fp32), thread per spot
-    float2 b2[KP / 2];
+    u64 bq[KP / 2];
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
-        const float4 b4 = ld4(c_tile + L::at(wrow + lane, q));
-        b2[2 * q] = make_float2(b4.x, b4.y);
-        b2[2 * q + 1] = make_float2(b4.z, b4.w);
+        const ulonglong2 b4 = *reinterpret_cast<const ulonglong2 *>(c_tile + L::at(wrow + lane, q));
+        bq[2 * q] = b4.x;
+        bq[2 * q + 1] = b4.y;
     }
     __syncwarp();
     // the warp's fp32 rows are free again: H rows stream into them asynchronously (LDGSTS, no registers)
@@ -458,19 +481,25 @@ bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
             for (int j = 0; j < 4; ++j) {
                 const int k = 4 * q + j;
                 if (k >= KP - 3 && k >= n_types) continue;
-                float2 a0 = make_float2(fmaf(lam, elem(ns4, j), elem(c4, j)), 0.f), a1 = make_float2(0.f, 0.f);
+                u64 a0 = pack2(fmaf(lam, elem(ns4, j), elem(c4, j)), 0.f), a1 = pack2(0.f, 0.f);
 #pragma unroll
                 for (int jj = 0; jj < KP / 2; ++jj) {
-                    const float2 g = make_float2(G.g[k * KP + 2 * jj], G.g[k * KP + 2 * jj + 1]);
-                    if (jj & 1) ffma2(a1, g, b2[jj]); else ffma2(a0, g, b2[jj]);
+                    const u64 g = *reinterpret_cast<const u64 *>(&G.g[k * KP + 2 * jj]);
+                    if (jj & 1) ffma2q(a1, g, bq[jj]); else ffma2q(a0, g, bq[jj]);
                 }
-                const float part = (a0.x + a0.y) + (a1.x + a1.y);
-                const float old = (k & 1) ? b2[k / 2].y : b2[k / 2].x;
+                float p0, p1, p2, p3, blo, bhi;
+                unpack2(a0, p0, p1);
+                unpack2(a1, p2, p3);
+                unpack2(bq[k / 2], blo, bhi);
+                const float part = (p0 + p1) + (p2 + p3);
+                const float old = (k & 1) ? bhi : blo;
                 const float den = G.diag[k] + lam_deg;
-                const float nv = den > 1e-10f ? fmaxf(0.f, __fdividef(part - rho, den)) : 0.f;
+                // max(0, soft(part, rho) / den) == max(0, (part - rho) / den) for den > 0; branch-free
+                const float cand = fmaxf(0.f, (part - rho) * rcp_fast(den));
+                const float nv = den > 1e-10f ? cand : 0.f;
                 dmax = fmaxf(dmax, fabsf(nv - old));
                 amax = fmaxf(amax, fabsf(old));
-                if (k & 1) b2[k / 2].y = nv; else b2[k / 2].x = nv;
+                bq[k / 2] = (k & 1) ? pack2(blo, nv) : pack2(nv, bhi);
                 set_elem(n4, j, nv);
             }
             st4(c_tile + L::at(trow, q), n4);
