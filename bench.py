@@ -295,7 +295,7 @@ def main():
         "gpu_launches": int(launches),
         "stage_ms": stage_ms,
         "roofline": {"bound": "hbm", "kernel": "bcd_sweep_kernel", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic(args.config, "bcd_sweep_kernel"),
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic(args.config, "bcd_sweep"),
                      "peak_source": peak_src,
                      "bytes_per_launch": sweep_bytes, "ms_per_launch": sweep_ms,
                      "sketch_kernel": {"achieved": sketch_gbs, "frac": sketch_gbs / peak,

@@ -314,8 +314,8 @@ __device__ __forceinline__ int gsw(int row)
     return GQ == 4 ? ((row >> 1) & 3) : (GQ == 2 ? ((row >> 2) & 1) : 0);
 }
 
-template <int KP, int NW>
-__global__ void __launch_bounds__(NW * 32, 768 / (NW * 32))
+template <int KP, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
 bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP> G,
                    const float *__restrict__ beta_in, float *__restrict__ beta_out,
                    const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
@@ -385,12 +385,12 @@ bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
         }
     }
     // own beta_old row -> registers (fp32), thread per spot
-    u64 bq[KP / 2];
+    float2 b2[KP / 2];
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
-        const ulonglong2 b4 = *reinterpret_cast<const ulonglong2 *>(c_tile + L::at(wrow + lane, q));
-        bq[2 * q] = b4.x;
-        bq[2 * q + 1] = b4.y;
+        const float4 b4 = ld4(c_tile + L::at(wrow + lane, q));
+        b2[2 * q] = make_float2(b4.x, b4.y);
+        b2[2 * q + 1] = make_float2(b4.z, b4.w);
     }
     __syncwarp();
     // the warp's fp32 rows are free again: H rows stream into them asynchronously (LDGSTS, no registers)
@@ -481,25 +481,19 @@ bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
             for (int j = 0; j < 4; ++j) {
                 const int k = 4 * q + j;
                 if (k >= KP - 3 && k >= n_types) continue;
-                u64 a0 = pack2(fmaf(lam, elem(ns4, j), elem(c4, j)), 0.f), a1 = pack2(0.f, 0.f);
+                float2 a0 = make_float2(fmaf(lam, elem(ns4, j), elem(c4, j)), 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
                 for (int jj = 0; jj < KP / 2; ++jj) {
-                    const u64 g = *reinterpret_cast<const u64 *>(&G.g[k * KP + 2 * jj]);
-                    if (jj & 1) ffma2q(a1, g, bq[jj]); else ffma2q(a0, g, bq[jj]);
+                    const float2 g = make_float2(G.g[k * KP + 2 * jj], G.g[k * KP + 2 * jj + 1]);
+                    if (jj & 1) ffma2(a1, g, b2[jj]); else ffma2(a0, g, b2[jj]);
                 }
-                float p0, p1, p2, p3, blo, bhi;
-                unpack2(a0, p0, p1);
-                unpack2(a1, p2, p3);
-                unpack2(bq[k / 2], blo, bhi);
-                const float part = (p0 + p1) + (p2 + p3);
-                const float old = (k & 1) ? bhi : blo;
+                const float part = (a0.x + a0.y) + (a1.x + a1.y);
+                const float old = (k & 1) ? b2[k / 2].y : b2[k / 2].x;
                 const float den = G.diag[k] + lam_deg;
-                // max(0, soft(part, rho) / den) == max(0, (part - rho) / den) for den > 0; branch-free
-                const float cand = fmaxf(0.f, (part - rho) * rcp_fast(den));
-                const float nv = den > 1e-10f ? cand : 0.f;
+                const float nv = den > 1e-10f ? fmaxf(0.f, __fdividef(part - rho, den)) : 0.f;
                 dmax = fmaxf(dmax, fabsf(nv - old));
                 amax = fmaxf(amax, fabsf(old));
-                bq[k / 2] = (k & 1) ? pack2(blo, nv) : pack2(nv, bhi);
+                if (k & 1) b2[k / 2].y = nv; else b2[k / 2].x = nv;
                 set_elem(n4, j, nv);
             }
             st4(c_tile + L::at(trow, q), n4);
@@ -813,23 +807,31 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
         FDB_LAUNCH_CHECK("bcd_sweep_kernel");
         return FDB_OK;
     };
-    if constexpr (KP <= 32 && KP % 8 == 0) {
+    if constexpr (KP % 8 == 0) {
         // fp16 neighbour values are admissible while the spatial term is a small part of the diagonal
         // (auto lambda: lam*deg = 0.5 % of G_kk); for strongly coupled problems stay in fp32
         float mean_diag = 0.f;
         for (int k = 0; k < n_types; ++k) mean_diag += host_gram[k * n_types + k];
         mean_diag /= (float)n_types;
         const bool weak_coupling = lam * 8.f <= 0.02f * mean_diag;
-        if ((variant == 0 && weak_coupling) || variant == 4) {   // halo-staged fp16 gather tile (default)
-            constexpr int NWH = 8, TILE = NWH * 32;
+        if ((variant == 0 && weak_coupling) || variant == 4 || variant == 6) {   // halo-staged fp16 gather tile
+            // patch size / residency by row width: 73 KB (Kp <= 32), 95 KB (Kp = 40), 55-72 KB at 128 spots (Kp >= 48)
+            constexpr int NWH = KP <= 40 ? 8 : 4;
+            constexpr int MINB = KP <= 32 ? 3 : (KP <= 40 ? 2 : 3);
+            constexpr int TILE = NWH * 32;
             const size_t smem = (size_t)TILE * TileLayout<KP>::S * 4 + (size_t)2 * TILE * (KP / 2) * 4 +
                                 (size_t)NWH * kIdxCap * 4 + (size_t)TILE * 4;
-            auto kern = bcd_sweep_h_kernel<KP, NWH>;
-            FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<(int)ceil_div(n_rows, TILE), TILE, smem, st>>>(h, G, beta_in, beta_out, indptr, indices, (int)n_rows,
-                                                                 n_types, lam, rho, tol, finalize, state);
-            FDB_LAUNCH_CHECK("bcd_sweep_h_kernel");
-            return FDB_OK;
+            auto run = [&](auto kern) -> int {
+                FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                kern<<<(int)ceil_div(n_rows, TILE), TILE, smem, st>>>(h, G, beta_in, beta_out, indptr, indices,
+                                                                     (int)n_rows, n_types, lam, rho, tol, finalize, state);
+                FDB_LAUNCH_CHECK("bcd_sweep_h_kernel");
+                return FDB_OK;
+            };
+            if constexpr (KP <= 32) {
+                if (variant == 6) return run(bcd_sweep_h_kernel<KP, NWH, 2>);   // tuning: 2 CTAs/SM, 126 registers
+            }
+            return run(bcd_sweep_h_kernel<KP, NWH, MINB>);
         }
     }
     if constexpr (KP <= 32) {
@@ -853,8 +855,7 @@ static int dispatch_sweep(const float *h, const float *host_gram, int n_types, c
     switch (fdb_padded_types(n_types)) {
         FDB_SWEEP_CASE(4) FDB_SWEEP_CASE(8) FDB_SWEEP_CASE(12) FDB_SWEEP_CASE(16)
         FDB_SWEEP_CASE(20) FDB_SWEEP_CASE(24) FDB_SWEEP_CASE(28) FDB_SWEEP_CASE(32)
-        FDB_SWEEP_CASE(36) FDB_SWEEP_CASE(40) FDB_SWEEP_CASE(44) FDB_SWEEP_CASE(48)
-        FDB_SWEEP_CASE(52) FDB_SWEEP_CASE(56) FDB_SWEEP_CASE(60) FDB_SWEEP_CASE(64)
+        FDB_SWEEP_CASE(40) FDB_SWEEP_CASE(48) FDB_SWEEP_CASE(56) FDB_SWEEP_CASE(64)
     default:
         set_error("n_types must be in [1, %d], got %d", FDB_MAX_TYPES, n_types);
         return FDB_ERR_UNSUPPORTED;

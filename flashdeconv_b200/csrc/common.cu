@@ -25,4 +25,10 @@ int cuda_fail(cudaError_t e, const char *what)
 FDB_API int fdb_abi_version(void) { return 1; }
 FDB_API const char *fdb_last_error(void) { return fdb::g_err; }
 FDB_API long long fdb_launch_count(void) { return fdb::g_launches; }
-FDB_API int fdb_padded_types(int n_types) { return n_types <= 0 ? 0 : (int)fdb::round_up(n_types, 4); }
+// rows are 16-byte aligned (multiple of 4 floats); above 32 types they are padded to a multiple of 8 so that the
+// half-precision gather rows of the sweep kernel are 16-byte aligned too
+FDB_API int fdb_padded_types(int n_types)
+{
+    if (n_types <= 0) return 0;
+    return (int)fdb::round_up(n_types, n_types > 32 ? 8 : 4);
+}
