@@ -26,23 +26,11 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include "fdb_common.cuh"
+#include "bcd_state.cuh"
 
 extern "C" __attribute__((visibility("default"))) int fdb_bcd_init(float *beta, int64_t n_rows, int32_t n_types, void *state, void *stream);
 
 namespace fdb {
-
-struct SolveState {                 // mirrors the 64-byte block documented in fdb200.h
-    unsigned max_diff_bits;
-    unsigned max_abs_bits;
-    unsigned arrived;
-    int sweeps;
-    int converged;
-    float rel_change;
-    float last_max_diff;
-    float last_max_abs;
-    int pad[8];
-};
-static_assert(sizeof(SolveState) == 64, "state block is 64 bytes");
 
 template <int KP>
 struct alignas(16) GramArg {
@@ -89,20 +77,6 @@ __device__ __forceinline__ float elem(const float4 &v, int j) { return j == 0 ? 
 __device__ __forceinline__ void set_elem(float4 &v, int j, float x)
 {
     if (j == 0) v.x = x; else if (j == 1) v.y = x; else if (j == 2) v.z = x; else v.w = x;
-}
-
-__device__ __forceinline__ void finalize_state(SolveState *st, float tol)
-{
-    const float md = __uint_as_float(st->max_diff_bits), ma = __uint_as_float(st->max_abs_bits);
-    const float rel = md / (ma + 1e-10f);
-    st->rel_change = rel;
-    st->last_max_diff = md;
-    st->last_max_abs = ma;
-    st->sweeps += 1;
-    if (rel < tol) st->converged = 1;
-    st->max_diff_bits = 0u;
-    st->max_abs_bits = 0u;
-    st->arrived = 0u;
 }
 
 constexpr int kIdxCap = 256;        // neighbour indices staged in shared memory per warp (32 spots)

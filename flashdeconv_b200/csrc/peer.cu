@@ -1,0 +1,145 @@
+// Multi-GPU solve loop over NVLink peer memory (no NCCL on the data path).
+//
+// Every rank's beta buffers live in a symmetric allocation that all peers have mapped (the host layer
+// obtains the mapping, e.g. torch symmetric memory / CUDA IPC, and passes the peers' base pointers).
+// Per sweep, on ONE stream and without host synchronisation:
+//   1. fdb_bcd_sweep on the rank's own rows (finalize = 0);
+//   2. peer_push_kernel: the boundary rows each neighbour needs are written STRAIGHT into that
+//      neighbour's halo slots over NVLink (128-byte rows, coalesced 16-byte stores);
+//   3. peer_sync_kernel: one thread per rank publishes this rank's two max-norm words and a sweep sequence
+//      number into every peer's comm block (fence.sys + release store), spins until every peer's
+//      sequence number has arrived here (acquire loads), then reduces the max norms and runs the stop
+//      test -- the MAX all-reduce of core/solver.py:395-397 and the halo hand-shake in one 1-block kernel.
+// Ordering argument (two beta buffers X, Y alternate): a rank starts sweep t+1 only after every peer's
+// flag t, which a peer writes after its sweep t and push t completed; so rows pushed for sweep t+1 can never
+// overwrite halo rows a peer is still reading in sweep t, and the rows read in sweep t+2 were pushed
+// before flag t+1.  The statistics slots are double-buffered by sweep parity for the same reason.
+//
+// Symmetric buffer layout (floats): [beta_a: cap_rows*Kp][beta_b: cap_rows*Kp][comm: kCommWords u32]
+//   comm: flags[kMaxRanks], stats[2][kMaxRanks][2]
+#include "bcd_state.cuh"
+
+extern "C" int fdb_bcd_sweep(const float *h, const float *host_gram, const float *beta_in, float *beta_out,
+                             const int32_t *indptr, const int32_t *indices, int64_t n_rows, int32_t n_types,
+                             float lambda, float rho_scaled, float tol, int32_t finalize, void *state, void *stream);
+extern "C" int fdb_bcd_init(float *beta, int64_t n_rows, int32_t n_types, void *state, void *stream);
+
+namespace fdb {
+
+constexpr int kMaxRanks = 16;
+constexpr int kCommWords = kMaxRanks + 2 * kMaxRanks * 2;      // 80 words; the host reserves 256
+
+struct PeerBases {
+    float *base[kMaxRanks];
+};
+
+__global__ void __launch_bounds__(256)
+peer_push_kernel(const float *__restrict__ beta_local, PeerBases pb, int64_t buf_off, const int32_t *__restrict__ src_row,
+                 const int32_t *__restrict__ dst_peer, const int64_t *__restrict__ dst_row, int64_t n_push, int chunks)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_push * chunks) return;
+    const int64_t e = t / chunks;
+    const int q = (int)(t - e * chunks);
+    const float4 v = *reinterpret_cast<const float4 *>(beta_local + ((int64_t)src_row[e] * chunks + q) * 4);
+    float *dst = pb.base[dst_peer[e]] + buf_off + (dst_row[e] * chunks + q) * 4;
+    *reinterpret_cast<float4 *>(dst) = v;
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(kMaxRanks)
+peer_sync_kernel(SolveState *st, PeerBases pb, int64_t comm_off, int rank, int world, unsigned seq, float tol)
+{
+    if (st->converged) return;                       // every rank converges at the same sweep (same reduced norms)
+    const int peer = threadIdx.x;
+    const int parity = (int)(seq & 1u);
+    __shared__ int timed_out;
+    if (threadIdx.x == 0) timed_out = 0;
+    __syncthreads();
+    if (peer < world) {
+        unsigned *pc = reinterpret_cast<unsigned *>(pb.base[peer] + comm_off);       // the peer's comm block
+        unsigned *slot = pc + kMaxRanks + (parity * kMaxRanks + rank) * 2;
+        __threadfence_system();                      // order after this rank's sweep + push (earlier kernels)
+        slot[0] = st->max_diff_bits;
+        slot[1] = st->max_abs_bits;
+        __threadfence_system();
+        st_release_sys(pc + rank, seq);
+        const unsigned *mine = reinterpret_cast<const unsigned *>(pb.base[rank] + comm_off);
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_sys(mine + peer) - seq) < 0) {
+            if (clock64() - t0 > 20000000000LL) { timed_out = 1; break; }            // ~10 s: a peer is gone
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (timed_out) { st->converged = 2; return; }                                // surfaced as an error by the host
+        const unsigned *mine = reinterpret_cast<const unsigned *>(pb.base[rank] + comm_off);
+        unsigned md = 0u, ma = 0u;
+        for (int p = 0; p < world; ++p) {
+            md = max(md, ld_acquire_sys(mine + kMaxRanks + (parity * kMaxRanks + p) * 2));
+            ma = max(ma, ld_acquire_sys(mine + kMaxRanks + (parity * kMaxRanks + p) * 2 + 1));
+        }
+        st->max_diff_bits = md;
+        st->max_abs_bits = ma;
+        finalize_state(st, tol);
+    }
+}
+
+}  // namespace fdb
+
+using namespace fdb;
+
+#define FDB_API extern "C" __attribute__((visibility("default")))
+
+FDB_API int64_t fdb_peer_comm_floats(void) { return 256; }
+
+FDB_API int fdb_bcd_solve_peer(const float *h, const float *host_gram, void *const *host_peer_base, int32_t rank,
+                               int32_t world, int64_t cap_rows, const int32_t *indptr, const int32_t *indices,
+                               int64_t n_own, int64_t n_total, int32_t n_types, float lambda, float rho_scaled,
+                               int32_t max_iter, float tol, void *state, int64_t n_push, const int32_t *push_src_row,
+                               const int32_t *push_peer, const int64_t *push_dst_row, uint32_t seq_base, void *stream)
+{
+    FDB_REQUIRE(host_peer_base && state, "null peer table / state");
+    FDB_REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world, "world must be in [1, %d]", kMaxRanks);
+    FDB_REQUIRE(n_own >= 0 && n_total >= n_own && n_total <= cap_rows && max_iter >= 0, "bad sizes");
+    FDB_REQUIRE(n_types >= 1 && n_types <= FDB_MAX_TYPES, "n_types must be in [1, %d], got %d", FDB_MAX_TYPES, n_types);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int kp = fdb_padded_types(n_types);
+    PeerBases pb;
+    for (int p = 0; p < kMaxRanks; ++p) pb.base[p] = p < world ? (float *)host_peer_base[p] : nullptr;
+    const int64_t off_a = 0, off_b = cap_rows * kp, off_comm = 2 * cap_rows * kp;
+    float *mine = pb.base[rank];
+    int rc = fdb_bcd_init(mine + off_a, n_total, n_types, state, stream);     // halo rows start at 1/K as well
+    if (rc) return rc;
+    rc = fdb_bcd_init(mine + off_b, n_total, n_types, nullptr, stream);
+    if (rc) return rc;
+    int64_t cur = off_a, nxt = off_b;
+    const int chunks = kp / 4;
+    for (int it = 0; it < max_iter; ++it) {
+        if (n_own > 0) {
+            rc = fdb_bcd_sweep(h, host_gram, mine + cur, mine + nxt, indptr, indices, n_own, n_types, lambda, rho_scaled,
+                               tol, 0, state, stream);
+            if (rc) return rc;
+        }
+        if (n_push > 0) {
+            peer_push_kernel<<<(int)ceil_div(n_push * chunks, 256), 256, 0, st>>>(mine + nxt, pb, nxt, push_src_row,
+                                                                                  push_peer, push_dst_row, n_push, chunks);
+            FDB_LAUNCH_CHECK("peer_push_kernel");
+        }
+        peer_sync_kernel<<<1, kMaxRanks, 0, st>>>((SolveState *)state, pb, off_comm, rank, world,
+                                                  seq_base + (unsigned)it + 1u, tol);
+        FDB_LAUNCH_CHECK("peer_sync_kernel");
+        const int64_t t = cur; cur = nxt; nxt = t;
+    }
+    return FDB_OK;
+}

@@ -27,6 +27,8 @@ import numpy as np
 
 
 _COMM_CACHE = {}
+_SYMM_CACHE = {}        # (floats, group id) -> (symmetric buffer, rendezvous handle, peer base pointers)
+_SEQ_BASE = 1           # sweep sequence numbers of the peer-memory hand-shake; identical on every rank
 
 
 def release_communicators():
@@ -38,6 +40,7 @@ def release_communicators():
     for comm in _COMM_CACHE.values():
         _native.lib.fdb_comm_destroy(comm)
     _COMM_CACHE.clear()
+    _SYMM_CACHE.clear()
 
 
 def tile_bounds(n: int, world: int, align: int = 256) -> List[Tuple[int, int]]:
@@ -149,7 +152,11 @@ class TiledPath:
         self.state = torch.zeros(16, dtype=torch.int32, device=self.dev)
         self.graph = None
         self.plan: Optional[TilePlan] = None
-        self.comm = self._native_comm()
+        import os
+        self.mode = os.environ.get("FDB_TILED_MODE", "peer")         # peer (NVLink peer memory) | nccl | torch
+        if os.environ.get("FDB_TILED_TORCH"):
+            self.mode = "torch"
+        self.comm = self._native_comm() if self.mode == "nccl" else None
 
     def _native_comm(self):
         """NCCL communicator owned by libfdb200 (the solve loop issues its collectives from C).  The unique id
@@ -193,7 +200,52 @@ class TiledPath:
         self.beta_a = t.empty((max(p.n_total, 1), self.Kp), dtype=t.float32, device=self.dev)
         self.beta_b = t.empty((max(p.n_total, 1), self.Kp), dtype=t.float32, device=self.dev)
         self.send_bufs = [t.empty((rows.numel(), self.Kp), dtype=t.float32, device=self.dev) for _, rows in p.send]
+        if self.mode == "peer":
+            try:
+                self._setup_peer()
+            except Exception as exc:          # no P2P mapping on this box: fall back to the NCCL loop
+                import warnings
+                warnings.warn(f"peer-memory halo exchange unavailable ({exc!r}); using NCCL send/recv")
+                self.mode = "nccl"
+                if self.comm is None:
+                    self.comm = self._native_comm()
         return self.graph
+
+    def _setup_peer(self):
+        """Symmetric beta buffers (mapped by every peer) + the push list for direct NVLink halo writes."""
+        import torch.distributed._symmetric_memory as symm_mem
+        t, p, dist = self.torch, self.plan, self.dist
+        cap = t.tensor([p.n_total], device=self.dev, dtype=t.int64)
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=self.group)
+        cap_rows = max(int(cap.item()), 1)
+        comm_floats = int(self.lib.fdb_peer_comm_floats())
+        total = 2 * cap_rows * self.Kp + comm_floats
+        key = (total, id(self.group))
+        if key not in _SYMM_CACHE:
+            buf = symm_mem.empty(total, dtype=t.float32, device=self.dev)
+            buf.zero_()
+            grp = self.group if self.group is not None else dist.group.WORLD
+            hdl = symm_mem.rendezvous(buf, grp)
+            t.cuda.synchronize()
+            dist.barrier(group=self.group)                       # every comm block is zero before anyone signals
+            _SYMM_CACHE[key] = (buf, hdl, [int(x) for x in hdl.buffer_ptrs])
+        self.symm_buf, self.symm_hdl, self.peer_ptrs = _SYMM_CACHE[key]
+        self.cap_rows = cap_rows
+        self.beta_a = self.symm_buf[: cap_rows * self.Kp].view(cap_rows, self.Kp)
+        self.beta_b = self.symm_buf[cap_rows * self.Kp: 2 * cap_rows * self.Kp].view(cap_rows, self.Kp)
+        # where do my boundary rows live in each neighbour's buffer?  (its n_own + the first slot of my slice there)
+        meta = [None] * self.world
+        dist.all_gather_object(meta, (p.n_own, {peer: first for peer, first, _ in p.recv}), group=self.group)
+        src, peers, dst = [], [], []
+        for peer, rows in p.send:
+            n_own_peer, firsts = meta[peer]
+            base = n_own_peer + firsts[self.rank]
+            src.append(rows.to(t.int32))
+            peers.append(t.full((rows.numel(),), peer, dtype=t.int32, device=self.dev))
+            dst.append(base + t.arange(rows.numel(), dtype=t.int64, device=self.dev))
+        cat = lambda xs, dt: (t.cat(xs) if xs else t.zeros(1, dtype=dt, device=self.dev)).contiguous()
+        self.n_push = int(sum(r.numel() for _, r in p.send))
+        self.push_src, self.push_peer, self.push_dst = cat(src, t.int32), cat(peers, t.int32), cat(dst, t.int64)
 
     def stage_sketch(self):
         c, tb, p = self.csr, self.tables, self.plan
@@ -235,6 +287,17 @@ class TiledPath:
         t, p, pl = self.torch, self.plan, self.pl
         st = self._stream()
         gram = self.gram32.ctypes.data_as(C.c_void_p)
+        if self.mode == "peer":
+            global _SEQ_BASE
+            bases = (C.c_void_p * self.world)(*self.peer_ptrs)
+            seq = _SEQ_BASE
+            _SEQ_BASE += int(max_iter) + 8
+            self.check(self.lib.fdb_bcd_solve_peer(
+                pl._ptr(self.h), gram, bases, self.rank, self.world, self.cap_rows, pl._ptr(p.indptr), pl._ptr(p.indices),
+                p.n_own, p.n_total, self.K, float(lam), float(rho_scaled), int(max_iter), float(tol), pl._ptr(self.state),
+                self.n_push, pl._ptr(self.push_src), pl._ptr(self.push_peer), pl._ptr(self.push_dst), seq, st),
+                "bcd_solve_peer")
+            return
         if self.comm is not None:
             i32, i64, vp = C.c_int32, C.c_int64, C.c_void_p
             nr, ns = len(p.recv), len(p.send)
@@ -267,6 +330,8 @@ class TiledPath:
 
     def read_state(self):
         st = self.state.cpu()
+        if int(st[4]) == 2:
+            raise RuntimeError("peer-memory halo exchange timed out waiting for another rank")
         return int(st[3]), bool(int(st[4])), float(st[5:6].view(self.torch.float32)[0])
 
     def current_beta(self, n_iter):

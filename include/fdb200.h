@@ -199,6 +199,21 @@ int fdb_bcd_solve_tiled(const float *h, const float *host_gram, float *beta_a, f
                         const int64_t *host_send_count, float *const *host_send_buf, void *comm,
                         void *stream);
 
+/* Peer-memory form of fdb_bcd_solve_tiled: no NCCL on the data path.  Every rank's beta buffers live in a
+ * symmetric allocation mapped by all peers; host_peer_base[p] is rank p's base pointer as seen from THIS
+ * process.  Layout (floats): beta_a [cap_rows x Kp], beta_b [cap_rows x Kp], comm [fdb_peer_comm_floats()],
+ * identical on all ranks (cap_rows >= every rank's n_total).  Per sweep: sweep own rows -> write the boundary
+ * rows straight into the neighbours' halo slots over NVLink (push_src_row[e] of this rank's buffer goes to row
+ * push_dst_row[e] of rank push_peer[e]'s buffer; device arrays) -> one 1-block kernel publishes the two
+ * max-norm words + a sequence number to every peer, waits for all peers' and applies the stop test.
+ * seq_base must grow by more than max_iter between successive solves on the same allocation. */
+int64_t fdb_peer_comm_floats(void);
+int fdb_bcd_solve_peer(const float *h, const float *host_gram, void *const *host_peer_base, int32_t rank,
+                       int32_t world, int64_t cap_rows, const int32_t *indptr, const int32_t *indices,
+                       int64_t n_own, int64_t n_total, int32_t n_types, float lambda, float rho_scaled,
+                       int32_t max_iter, float tol, void *state, int64_t n_push, const int32_t *push_src_row,
+                       const int32_t *push_peer, const int64_t *push_dst_row, uint32_t seq_base, void *stream);
+
 /* Multi-GPU helpers: gather / scatter whole beta rows by index list (halo exchange staging). */
 int fdb_rows_gather(const float *src, const int32_t *rows, int64_t n_list, int32_t row_floats,
                     float *dst, void *stream);

@@ -40,7 +40,7 @@ def main():
     flags = torch.tensor([int(ok), halo], device="cuda")
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"tiled x{world}: max|dprop|={err:.2e} max|dbeta|={berr:.2e} sweeps={info['n_iterations']} "
+        print(f"tiled x{world} [{tp.mode}]: max|dprop|={err:.2e} max|dbeta|={berr:.2e} sweeps={info['n_iterations']} "
               f"obj={info['final_objective']:.6g} vs {single.info['final_objective']:.6g} min_halo={int(flags[1])} "
               f"{'OK' if int(flags[0]) else 'MISMATCH'}")
     dist.destroy_process_group()
