@@ -58,7 +58,8 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
 }
 
 __global__ void __launch_bounds__(kMaxRanks)
-peer_sync_kernel(SolveState *st, PeerBases pb, int64_t comm_off, int rank, int world, unsigned seq, float tol)
+peer_sync_kernel(SolveState *st, PeerBases pb, int64_t comm_off, int rank, int world, unsigned seq, float tol,
+                 int do_finalize)
 {
     if (st->converged) return;                       // every rank converges at the same sweep (same reduced norms)
     const int peer = threadIdx.x;
@@ -83,6 +84,7 @@ peer_sync_kernel(SolveState *st, PeerBases pb, int64_t comm_off, int rank, int w
     __syncthreads();
     if (threadIdx.x == 0) {
         if (timed_out) { st->converged = 2; return; }                                // surfaced as an error by the host
+        if (!do_finalize) return;                                                    // start-of-solve rendezvous only
         const unsigned *mine = reinterpret_cast<const unsigned *>(pb.base[rank] + comm_off);
         unsigned md = 0u, ma = 0u;
         for (int p = 0; p < world; ++p) {
@@ -119,10 +121,14 @@ FDB_API int fdb_bcd_solve_peer(const float *h, const float *host_gram, void *con
     for (int p = 0; p < kMaxRanks; ++p) pb.base[p] = p < world ? (float *)host_peer_base[p] : nullptr;
     const int64_t off_a = 0, off_b = cap_rows * kp, off_comm = 2 * cap_rows * kp;
     float *mine = pb.base[rank];
-    int rc = fdb_bcd_init(mine + off_a, n_total, n_types, state, stream);     // halo rows start at 1/K as well
+    // beta_a (own + halo rows) starts at 1/K.  beta_b is NOT initialised: its own rows are written by sweep 1 and
+    // its halo rows by the peers' first push, which may arrive before this rank gets here.
+    int rc = fdb_bcd_init(mine + off_a, n_total, n_types, state, stream);
     if (rc) return rc;
-    rc = fdb_bcd_init(mine + off_b, n_total, n_types, nullptr, stream);
-    if (rc) return rc;
+    // start-of-solve rendezvous: nobody pushes rows before every rank has initialised its buffers and finished
+    // reading the previous solve's result (those kernels precede this one in stream order)
+    peer_sync_kernel<<<1, kMaxRanks, 0, st>>>((SolveState *)state, pb, off_comm, rank, world, seq_base, tol, 0);
+    FDB_LAUNCH_CHECK("peer_sync_kernel");
     int64_t cur = off_a, nxt = off_b;
     const int chunks = kp / 4;
     for (int it = 0; it < max_iter; ++it) {
@@ -137,7 +143,7 @@ FDB_API int fdb_bcd_solve_peer(const float *h, const float *host_gram, void *con
             FDB_LAUNCH_CHECK("peer_push_kernel");
         }
         peer_sync_kernel<<<1, kMaxRanks, 0, st>>>((SolveState *)state, pb, off_comm, rank, world,
-                                                  seq_base + (unsigned)it + 1u, tol);
+                                                  seq_base + (unsigned)it + 1u, tol, 1);
         FDB_LAUNCH_CHECK("peer_sync_kernel");
         const int64_t t = cur; cur = nxt; nxt = t;
     }
