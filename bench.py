@@ -229,6 +229,9 @@ def main():
     value = n / (ms_per_step * 1e-3)                # strong scaling: the N ranks share ONE n-spot problem
 
     halo_rows = int(path.plan.n_halo) if distributed else 0
+    tiled_mode = {"peer": "direct NVLink peer-memory row pushes + flag/max-norm hand-shake kernel (no NCCL on the data path)",
+                  "nccl": "ncclSend/ncclRecv + MAX all-reduce issued from the native loop",
+                  "torch": "torch.distributed isend/irecv + all_reduce"}[path.mode] if distributed else ""
     own_rows = int(path.plan.n_own) if distributed else n
     # ---- end to end through the host-buffer call ---------------------------------------
     host = pipeline.HostCSR(data["host_indptr"], data["host_indices"], data["host_data"], (n, G))
@@ -288,7 +291,7 @@ def main():
                    "mean_degree": deg, "sweeps": info["n_iterations"], "converged": info["converged"],
                    "l2": "inputs_exceed_l2",
                    "multi_gpu": (f"{world} spatial tiles, halo exchange per sweep (rank 0: {own_rows} own + {halo_rows} "
-                                 "halo rows), NCCL send/recv + MAX all-reduce") if world > 1 else "single"},
+                                 f"halo rows), {tiled_mode}") if world > 1 else "single"},
         "clocks": clocks.summary(),
         "e2e": {"value": n / e2e_s, "unit": "spots/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s},
