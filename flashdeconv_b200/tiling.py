@@ -71,36 +71,46 @@ class TilePlan:
 
 
 def plan_tile(indptr, indices, bounds: List[Tuple[int, int]], rank: int) -> TilePlan:
-    """Local adjacency + halo maps for `rank` from the replicated global CSR (torch tensors, any device)."""
+    """Local adjacency + halo maps for `rank` from the replicated global CSR (torch tensors, any device).
+
+    Only the rank's own rows are scanned: the graph is undirected, so the rows a peer needs from this rank are
+    exactly this rank's rows that have a neighbour owned by that peer."""
     import torch
     lo, hi = bounds[rank]
     dev = indices.device
-    ip = indptr.to(torch.int64)
-    e0, e1 = int(ip[lo]), int(ip[hi])
+    n_own = hi - lo
+    edge_range = indptr[lo:hi + 1].to(torch.int64)
+    e0, e1 = (int(v) for v in edge_range[[0, -1]].tolist()) if n_own else (0, 0)
     nbr = indices[e0:e1].to(torch.int64)
+    local_ptr = (edge_range - e0)
     outside = (nbr < lo) | (nbr >= hi)
-    halo_global = torch.unique(nbr[outside])                       # sorted ascending
-    n_own, n_halo = hi - lo, int(halo_global.numel())
+    cross = torch.nonzero(outside).flatten()                      # my edges that leave the tile
+    cross_nbr = nbr[cross]
+    halo_global = torch.unique(cross_nbr)                          # sorted ascending
+    n_halo = int(halo_global.numel())
     local = nbr - lo
     if n_halo:
-        local = torch.where(outside, n_own + torch.searchsorted(halo_global, nbr), local)
+        local[cross] = n_own + torch.searchsorted(halo_global, cross_nbr)
     recv, send = [], []
-    starts = torch.tensor([b[0] for b in bounds] + [bounds[-1][1]], device=dev, dtype=torch.int64)
     if n_halo:
-        owner_edges = torch.searchsorted(halo_global, starts)       # halo rows are grouped by owner
+        starts = torch.tensor([b[0] for b in bounds] + [bounds[-1][1]], device=dev, dtype=torch.int64)
+        owner_edges = torch.searchsorted(halo_global, starts).tolist()       # halo rows are grouped by owner
         for peer in range(len(bounds)):
-            a, b = int(owner_edges[peer]), int(owner_edges[peer + 1])
+            a, b = owner_edges[peer], owner_edges[peer + 1]
             if peer != rank and b > a:
                 recv.append((peer, a, b - a))
-    for peer, (plo, phi) in enumerate(bounds):
-        if peer == rank or phi <= plo:
-            continue
-        pe0, pe1 = int(ip[plo]), int(ip[phi])
-        pn = indices[pe0:pe1].to(torch.int64)
-        mine = torch.unique(pn[(pn >= lo) & (pn < hi)])             # what `peer` needs from me, ascending
-        if mine.numel():
-            send.append((peer, (mine - lo).to(torch.int32).contiguous()))
-    return TilePlan(rank, lo, hi, n_own, n_halo, (ip[lo:hi + 1] - e0).to(torch.int32).contiguous(),
+        # (owner of the outside neighbour, my row) pairs -> per-peer ascending send lists
+        cross_row = torch.searchsorted(local_ptr, cross, right=True) - 1     # local row of each crossing edge
+        cross_owner = torch.searchsorted(starts, cross_nbr, right=True) - 1
+        pair = torch.unique(cross_owner * n_own + cross_row)                  # sorted by (owner, row)
+        owner, row = pair // n_own, pair % n_own
+        cuts = torch.searchsorted(owner, torch.arange(len(bounds) + 1, device=dev, dtype=torch.int64)).tolist()
+        rows32 = row.to(torch.int32)
+        for peer in range(len(bounds)):
+            a, b = cuts[peer], cuts[peer + 1]
+            if peer != rank and b > a:
+                send.append((peer, rows32[a:b].contiguous()))
+    return TilePlan(rank, lo, hi, n_own, n_halo, local_ptr.to(torch.int32).contiguous(),
                     local.to(torch.int32).contiguous(), halo_global, recv, send)
 
 
@@ -215,9 +225,14 @@ class TiledPath:
         """Symmetric beta buffers (mapped by every peer) + the push list for direct NVLink halo writes."""
         import torch.distributed._symmetric_memory as symm_mem
         t, p, dist = self.torch, self.plan, self.dist
-        cap = t.tensor([p.n_total], device=self.dev, dtype=t.int64)
-        dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=self.group)
-        cap_rows = max(int(cap.item()), 1)
+        # one small all-gather: every rank's (n_own, n_total, first halo slot reserved for each peer)
+        mine = [p.n_own, p.n_total] + [-1] * self.world
+        for peer, first, _ in p.recv:
+            mine[2 + peer] = first
+        table = t.empty((self.world, self.world + 2), dtype=t.int64, device=self.dev)
+        dist.all_gather_into_tensor(table, t.tensor(mine, dtype=t.int64, device=self.dev), group=self.group)
+        meta = table.cpu().tolist()
+        cap_rows = max(max(row[1] for row in meta), 1)
         comm_floats = int(self.lib.fdb_peer_comm_floats())
         total = 2 * cap_rows * self.Kp + comm_floats
         key = (total, id(self.group))
@@ -234,12 +249,9 @@ class TiledPath:
         self.beta_a = self.symm_buf[: cap_rows * self.Kp].view(cap_rows, self.Kp)
         self.beta_b = self.symm_buf[cap_rows * self.Kp: 2 * cap_rows * self.Kp].view(cap_rows, self.Kp)
         # where do my boundary rows live in each neighbour's buffer?  (its n_own + the first slot of my slice there)
-        meta = [None] * self.world
-        dist.all_gather_object(meta, (p.n_own, {peer: first for peer, first, _ in p.recv}), group=self.group)
         src, peers, dst = [], [], []
         for peer, rows in p.send:
-            n_own_peer, firsts = meta[peer]
-            base = n_own_peer + firsts[self.rank]
+            base = meta[peer][0] + meta[peer][2 + self.rank]
             src.append(rows.to(t.int32))
             peers.append(t.full((rows.numel(),), peer, dtype=t.int32, device=self.dev))
             dst.append(base + t.arange(rows.numel(), dtype=t.int64, device=self.dev))
