@@ -29,21 +29,23 @@ SIGNATURES = {
                                   C.POINTER(_i64), C.POINTER(_f64), _vp, _i64, _vp]),
     "fdb_graph_to_input_order": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
     "fdb_bcd_init": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
-    "fdb_bcd_sweep": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _f32, _i32, _vp, _vp]),
+    "fdb_bcd_sweep": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _f32, _i32, _vp, _vp, _vp]),
+    "fdb_bcd_plan_bytes": (_i64, [_i64, _i64, _i32]),
+    "fdb_bcd_plan_build": (C.c_int, [_vp, _vp, _i64, _i64, _i32, _vp, _i64, _vp]),
     "fdb_bcd_finalize": (C.c_int, [_vp, _f32, _vp]),
-    "fdb_bcd_solve": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _i32, _f32, _vp, _vp]),
+    "fdb_bcd_solve": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _i32, _f32, _vp, _vp, _vp]),
     "fdb_objective_terms": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "fdb_finish": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "fdb_gene_moments_csr": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "fdb_rows_gather": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "fdb_peer_comm_floats": (_i64, []),
     "fdb_bcd_solve_peer": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _i32, _f32,
-                                     _vp, _i64, _vp, _vp, _vp, C.c_uint32, _vp]),
+                                     _vp, _i64, _vp, _vp, _vp, C.c_uint32, _vp, _vp]),
     "fdb_comm_unique_id": (C.c_int, [C.c_char_p]),
     "fdb_comm_init": (C.c_int, [_i32, _i32, C.c_char_p, C.POINTER(_vp)]),
     "fdb_comm_destroy": (C.c_int, [_vp]),
     "fdb_bcd_solve_tiled": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _i32, _f32, _vp,
-                                      _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                      _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 

@@ -288,11 +288,82 @@ __device__ __forceinline__ int gsw(int row)
     return GQ == 4 ? ((row >> 1) & 3) : (GQ == 2 ? ((row >> 2) & 1) : 0);
 }
 
+// ---- gather plan (built once per solve: the graph does not change between sweeps) ----------------------
+// For every CTA patch of `TILE` spots: the out-of-patch neighbour rows it needs (deduplicated, at most HCAP
+// = TILE of them) and, per neighbour reference in CSR order, a 16-bit code = row of the CTA's gather tile
+// (patch row, or TILE + halo slot) or 0xFFFF when the patch needs more than HCAP foreign rows.
+constexpr int kPlanHash = 1024;
+constexpr unsigned short kCodeSlow = 0xFFFF;
+
+struct PlanView {
+    const int32_t *halo_cnt;      // [n_ctas]
+    const int32_t *halo_rows;     // [n_ctas * HCAP]
+    const uint16_t *codes;        // [nnz]
+};
+
+__host__ __device__ inline int64_t plan_off_cnt() { return 64; }
+__host__ __device__ inline int64_t plan_off_rows(int64_t n_ctas) { return 64 + round_up(n_ctas * 4, 16); }
+__host__ __device__ inline int64_t plan_off_codes(int64_t n_ctas, int tile) { return plan_off_rows(n_ctas) + n_ctas * tile * 4; }
+
+template <int TILE>
+__global__ void __launch_bounds__(TILE)
+bcd_plan_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, int n_rows,
+                int32_t *__restrict__ halo_cnt, int32_t *__restrict__ halo_rows, uint16_t *__restrict__ codes)
+{
+    constexpr int HCAP = TILE;
+    __shared__ int keys[kPlanHash];
+    __shared__ int slots[kPlanHash];
+    __shared__ int count;
+    for (int i = threadIdx.x; i < kPlanHash; i += TILE) keys[i] = -1;
+    if (threadIdx.x == 0) count = 0;
+    __syncthreads();
+    const int tile_base = blockIdx.x * TILE;
+    const int row = tile_base + threadIdx.x;
+    int s = 0, e = 0;
+    if (row < n_rows) { s = indptr[row]; e = indptr[row + 1]; }
+    auto probe = [&](int g, bool insert) -> int {            // returns the table position of g, or -1
+        unsigned hpos = ((unsigned)g * 2654435761u) >> 22;    // 10 bits
+        for (int t = 0; t < kPlanHash; ++t) {
+            const int cur = insert ? atomicCAS(&keys[hpos], -1, g) : keys[hpos];
+            if (cur == g || (insert && cur == -1)) return (int)hpos;
+            if (!insert && cur == -1) return -1;
+            hpos = (hpos + 1) & (kPlanHash - 1);
+        }
+        return -1;
+    };
+    for (int j = s; j < e; ++j) {
+        const int g = indices[j];
+        if ((unsigned)(g - tile_base) >= (unsigned)TILE) probe(g, true);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kPlanHash; i += TILE) {
+        if (keys[i] >= 0) {
+            const int slot = atomicAdd(&count, 1);
+            slots[i] = slot;
+            if (slot < HCAP) halo_rows[(int64_t)blockIdx.x * HCAP + slot] = keys[i];
+        }
+    }
+    __syncthreads();
+    for (int j = s; j < e; ++j) {
+        const int g = indices[j];
+        const int rel = g - tile_base;
+        unsigned short code;
+        if ((unsigned)rel < (unsigned)TILE) {
+            code = (unsigned short)rel;
+        } else {
+            const int pos = probe(g, false);
+            code = (pos >= 0 && slots[pos] < HCAP) ? (unsigned short)(TILE + slots[pos]) : kCodeSlow;
+        }
+        codes[j] = code;
+    }
+    if (threadIdx.x == 0) halo_cnt[blockIdx.x] = min(count, HCAP);
+}
+
 template <int KP, int NW, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB)
 bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP> G,
                    const float *__restrict__ beta_in, float *__restrict__ beta_out,
-                   const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                   const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, PlanView plan,
                    int n_rows, int n_types, float lam, float rho, float tol, int finalize, SolveState *state)
 {
     static_assert(KP % 8 == 0, "half gather rows need Kp % 8 == 0");
@@ -305,21 +376,28 @@ bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
     extern __shared__ __align__(16) float sweep_smem[];
     float *c_tile = sweep_smem;                                                   // TILE x S fp32
     uint32_t *g_tile = reinterpret_cast<uint32_t *>(sweep_smem + TILE * S);       // (TILE + HCAP) x GROW words
-    int *idx_tile = reinterpret_cast<int *>(g_tile + (TILE + HCAP) * GROW);       // NW x kIdxCap
-    int *halo_src = idx_tile + NW * kIdxCap;                                      // HCAP global row ids
+    uint16_t *idx_tile = reinterpret_cast<uint16_t *>(g_tile + (TILE + HCAP) * GROW);   // NW x kIdxCap codes
     __shared__ unsigned red[2][NW];
-    __shared__ int halo_count;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tile_base = blockIdx.x * TILE;
     const int wrow = warp * 32;
-    int *iw = idx_tile + warp * kIdxCap;
-    if (threadIdx.x == 0) halo_count = 0;
+    uint16_t *iw = idx_tile + warp * kIdxCap;
 
-    // ---------------- step 0: row pointers; the warp's beta_old rows go to both tiles (fp32 + fp16)
+    // ---------------- step 0: everything this patch reads from global is requested up front:
+    //   row pointers, the warp's beta_old rows (-> fp32 tile + fp16 gather tile), the patch's foreign halo
+    //   rows (-> fp16 gather tile extension) and the warp's slice of neighbour codes
     const int my_row = tile_base + wrow + lane;
     int my_s = 0, my_e = 0;
     if (my_row < n_rows) { my_s = __ldg(indptr + my_row); my_e = __ldg(indptr + my_row + 1); }
+    const int n_halo = __ldg(plan.halo_cnt + blockIdx.x);
+    auto to_gather = [&](int grow, int q, const float4 bb) {
+        const __half2 lo = __floats2half2_rn(bb.x, bb.y), hi = __floats2half2_rn(bb.z, bb.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<const uint32_t *>(&lo);
+        pk.y = *reinterpret_cast<const uint32_t *>(&hi);
+        *reinterpret_cast<uint2 *>(g_tile + grow * GROW + 4 * ((q >> 1) ^ gsw<GQ>(grow)) + 2 * (q & 1)) = pk;
+    };
 #pragma unroll
     for (int i = 0; i < Q; ++i) {
         const int idx = lane + 32 * i;
@@ -328,37 +406,24 @@ bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
         float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p < n_rows) bb = ld4(beta_in + (size_t)p * KP + 4 * q);
         st4(c_tile + L::at(wrow + lr, q), bb);
-        const __half2 lo = __floats2half2_rn(bb.x, bb.y), hi = __floats2half2_rn(bb.z, bb.w);
-        uint2 pk;
-        pk.x = *reinterpret_cast<const uint32_t *>(&lo);
-        pk.y = *reinterpret_cast<const uint32_t *>(&hi);
-        *reinterpret_cast<uint2 *>(g_tile + (wrow + lr) * GROW + 4 * ((q >> 1) ^ gsw<GQ>(wrow + lr)) + 2 * (q & 1)) = pk;
+        to_gather(wrow + lr, q, bb);
+    }
+    for (int idx = threadIdx.x; idx < n_halo * Q; idx += TILE) {
+        const int slot = idx / Q, q = idx - slot * Q;
+        const int g = __ldg(plan.halo_rows + (size_t)blockIdx.x * HCAP + slot);
+        to_gather(TILE + slot, q, ld4(beta_in + (size_t)g * KP + 4 * q));
     }
     const int my_deg = my_e - my_s;
     const int ibase = __shfl_sync(kFull, my_s, 0);
     const int icnt = __reduce_max_sync(kFull, my_e - ibase);
     const bool staged = icnt <= kIdxCap;
     if (staged)
-        for (int t = lane; t < icnt; t += 32) iw[t] = __ldg(indices + ibase + t);
-    __syncthreads();                                     // halo_count = 0 visible; tiles + index slices staged
+        for (int t = lane; t < icnt; t += 32) iw[t] = plan.codes[ibase + t];
+    __syncthreads();                                     // tiles, halo rows and code slices are in shared memory
     if (already_converged) return;                       // uniform across the grid
 
-    // ---------------- step 1: turn neighbour ids into gather-tile rows; out-of-patch ones get a halo slot
+    // ---------------- step 1: own beta_old row -> registers (fp32), thread per spot
     const int rs = my_s - ibase;
-    if (staged) {
-        for (int u = 0; u < my_deg; ++u) {
-            const int g = iw[rs + u];
-            const int rel = g - tile_base;
-            int code = rel;
-            if ((unsigned)rel >= (unsigned)TILE) {
-                const int slot = atomicAdd(&halo_count, 1);
-                if (slot < HCAP) { halo_src[slot] = g; code = TILE + slot; }
-                else code = -(g + 1);                    // no slot left: that row is read from global (slow path)
-            }
-            iw[rs + u] = code;
-        }
-    }
-    // own beta_old row -> registers (fp32), thread per spot
     float2 b2[KP / 2];
 #pragma unroll
     for (int q = 0; q < Q; ++q) {
@@ -368,7 +433,7 @@ bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
     }
     __syncwarp();
     // the warp's fp32 rows are free again: H rows stream into them asynchronously (LDGSTS, no registers)
-    // while the halo is fetched and the neighbour sums are formed
+    // while the neighbour sums are formed
 #pragma unroll
     for (int i = 0; i < Q; ++i) {
         const int idx = lane + 32 * i;
@@ -382,21 +447,6 @@ bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
         }
     }
     asm volatile("cp.async.commit_group;");
-    __syncthreads();                                     // halo list complete
-    // halo rows: fetched once per CTA, coalesced (Q lanes per 128-byte row), converted to fp16
-    {
-        const int n_halo = min(halo_count, HCAP);
-        for (int idx = threadIdx.x; idx < n_halo * Q; idx += TILE) {
-            const int slot = idx / Q, q = idx - slot * Q;
-            const float4 bb = ld4(beta_in + (size_t)halo_src[slot] * KP + 4 * q);
-            const __half2 lo = __floats2half2_rn(bb.x, bb.y), hi = __floats2half2_rn(bb.z, bb.w);
-            uint2 pk;
-            pk.x = *reinterpret_cast<const uint32_t *>(&lo);
-            pk.y = *reinterpret_cast<const uint32_t *>(&hi);
-            *reinterpret_cast<uint2 *>(g_tile + (TILE + slot) * GROW + 4 * ((q >> 1) ^ gsw<GQ>(TILE + slot)) + 2 * (q & 1)) = pk;
-        }
-    }
-    __syncthreads();                                     // halo rows visible
 
     // ---------------- step 2: neighbour sums from the fp16 gather tile, one spot per lane
     __half2 acc[KP / 2];
@@ -408,11 +458,11 @@ bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
 #pragma unroll 1
         for (int u = 0; u < maxdeg; ++u) {
             const bool has = u < my_deg;
-            int code = own;
-            if (has) code = staged ? iw[rs + u] : -(__ldg(indices + my_s + u) + 1);
-            if (__any_sync(kFull, code < 0)) {           // rare: halo overflow / unstaged list -> fp32 row from global
-                if (code < 0) {
-                    const float *src = beta_in + (size_t)(-code - 1) * KP;
+            unsigned code = own;
+            if (has) code = staged ? iw[rs + u] : plan.codes[my_s + u];
+            if (__any_sync(kFull, code == kCodeSlow)) {  // rare: more foreign rows than halo slots -> fp32 row from global
+                if (code == kCodeSlow) {
+                    const float *src = beta_in + (size_t)__ldg(indices + my_s + u) * KP;
 #pragma unroll
                     for (int q = 0; q < Q; ++q) {
                         const float4 v = ld4(src + 4 * q);
@@ -422,9 +472,9 @@ bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
                 }
             }
             // lanes without a (shared-memory) neighbour this round re-read their own row with weight 0
-            const bool use = has && code >= 0;
+            const bool use = has && code != kCodeSlow;
             const __half2 m = use ? __floats2half2_rn(1.f, 1.f) : __floats2half2_rn(0.f, 0.f);
-            const int grow = use ? code : own;
+            const int grow = use ? (int)code : own;
             const uint4 *row = reinterpret_cast<const uint4 *>(g_tile + grow * GROW);
             const int sw = gsw<GQ>(grow);
 #pragma unroll
@@ -744,7 +794,8 @@ bcd_init_kernel(float *__restrict__ beta, int64_t n_rows, int kp, int n_types, S
 template <int KP>
 static int launch_sweep(const float *h, const float *host_gram, int n_types, const float *beta_in,
                         float *beta_out, const int32_t *indptr, const int32_t *indices, int64_t n_rows,
-                        float lam, float rho, float tol, int finalize, SolveState *state, cudaStream_t st)
+                        float lam, float rho, float tol, int finalize, SolveState *state, const void *plan,
+                        cudaStream_t st)
 {
     GramArg<KP> G;
     for (int i = 0; i < KP * KP; ++i) G.g[i] = 0.f;
@@ -788,17 +839,23 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
         for (int k = 0; k < n_types; ++k) mean_diag += host_gram[k * n_types + k];
         mean_diag /= (float)n_types;
         const bool weak_coupling = lam * 8.f <= 0.02f * mean_diag;
-        if ((variant == 0 && weak_coupling) || variant == 4 || variant == 6) {   // halo-staged fp16 gather tile
+        if (plan != nullptr && ((variant == 0 && weak_coupling) || variant == 4 || variant == 6)) {   // halo-staged fp16 gather tile
             // patch size / residency by row width: 73 KB (Kp <= 32), 95 KB (Kp = 40), 55-72 KB at 128 spots (Kp >= 48)
             constexpr int NWH = KP <= 40 ? 8 : 4;
             constexpr int MINB = KP <= 32 ? 3 : (KP <= 40 ? 2 : 3);
             constexpr int TILE = NWH * 32;
             const size_t smem = (size_t)TILE * TileLayout<KP>::S * 4 + (size_t)2 * TILE * (KP / 2) * 4 +
-                                (size_t)NWH * kIdxCap * 4 + (size_t)TILE * 4;
+                                (size_t)NWH * kIdxCap * 2;
+            const int64_t n_ctas = ceil_div(n_rows, TILE);
+            const char *pbase = (const char *)plan;
+            PlanView pv;
+            pv.halo_cnt = (const int32_t *)(pbase + plan_off_cnt());
+            pv.halo_rows = (const int32_t *)(pbase + plan_off_rows(n_ctas));
+            pv.codes = (const uint16_t *)(pbase + plan_off_codes(n_ctas, TILE));
             auto run = [&](auto kern) -> int {
                 FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                kern<<<(int)ceil_div(n_rows, TILE), TILE, smem, st>>>(h, G, beta_in, beta_out, indptr, indices,
-                                                                     (int)n_rows, n_types, lam, rho, tol, finalize, state);
+                kern<<<(int)n_ctas, TILE, smem, st>>>(h, G, beta_in, beta_out, indptr, indices, pv, (int)n_rows,
+                                                      n_types, lam, rho, tol, finalize, state);
                 FDB_LAUNCH_CHECK("bcd_sweep_h_kernel");
                 return FDB_OK;
             };
@@ -820,12 +877,13 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
 
 static int dispatch_sweep(const float *h, const float *host_gram, int n_types, const float *beta_in,
                           float *beta_out, const int32_t *indptr, const int32_t *indices, int64_t n_rows,
-                          float lam, float rho, float tol, int finalize, SolveState *state, cudaStream_t st)
+                          float lam, float rho, float tol, int finalize, SolveState *state, const void *plan,
+                          cudaStream_t st)
 {
 #define FDB_SWEEP_CASE(KP_)                                                                            \
     case KP_:                                                                                          \
         return launch_sweep<KP_>(h, host_gram, n_types, beta_in, beta_out, indptr, indices, n_rows,    \
-                                 lam, rho, tol, finalize, state, st);
+                                 lam, rho, tol, finalize, state, plan, st);
     switch (fdb_padded_types(n_types)) {
         FDB_SWEEP_CASE(4) FDB_SWEEP_CASE(8) FDB_SWEEP_CASE(12) FDB_SWEEP_CASE(16)
         FDB_SWEEP_CASE(20) FDB_SWEEP_CASE(24) FDB_SWEEP_CASE(28) FDB_SWEEP_CASE(32)
@@ -968,15 +1026,53 @@ static int check_solver_args(const void *h, const void *gram, const void *a, con
     return FDB_OK;
 }
 
+static int plan_tile_rows(int n_types)
+{
+    const int kp = fdb_padded_types(n_types);
+    if (kp % 8 != 0) return 0;                         // no half gather tile for this row width: no plan needed
+    return kp <= 40 ? 256 : 128;                       // must match the dispatcher in launch_sweep
+}
+
+extern "C" __attribute__((visibility("default"))) int64_t fdb_bcd_plan_bytes(int64_t n_rows, int64_t nnz, int32_t n_types)
+{
+    const int tile = plan_tile_rows(n_types);
+    if (tile == 0 || n_rows <= 0) return 0;
+    const int64_t n_ctas = ceil_div(n_rows, tile);
+    return round_up(plan_off_codes(n_ctas, tile) + 2 * (nnz > 0 ? nnz : 1), 256);
+}
+
+extern "C" __attribute__((visibility("default"))) int fdb_bcd_plan_build(const int32_t *indptr, const int32_t *indices, int64_t n_rows,
+                                          int64_t nnz, int32_t n_types, void *plan, int64_t plan_bytes, void *stream)
+{
+    const int tile = plan_tile_rows(n_types);
+    if (tile == 0 || n_rows <= 0) return FDB_OK;
+    FDB_REQUIRE(indptr && indices && plan, "null pointer");
+    if (plan_bytes < fdb_bcd_plan_bytes(n_rows, nnz, n_types)) {
+        set_error("plan buffer too small: need %lld bytes", (long long)fdb_bcd_plan_bytes(n_rows, nnz, n_types));
+        return FDB_ERR_WORKSPACE;
+    }
+    const int64_t n_ctas = ceil_div(n_rows, tile);
+    char *pbase = (char *)plan;
+    int32_t *cnt = (int32_t *)(pbase + plan_off_cnt());
+    int32_t *rows = (int32_t *)(pbase + plan_off_rows(n_ctas));
+    uint16_t *codes = (uint16_t *)(pbase + plan_off_codes(n_ctas, tile));
+    if (tile == 256)
+        bcd_plan_kernel<256><<<(int)n_ctas, 256, 0, (cudaStream_t)stream>>>(indptr, indices, (int)n_rows, cnt, rows, codes);
+    else
+        bcd_plan_kernel<128><<<(int)n_ctas, 128, 0, (cudaStream_t)stream>>>(indptr, indices, (int)n_rows, cnt, rows, codes);
+    FDB_LAUNCH_CHECK("bcd_plan_kernel");
+    return FDB_OK;
+}
+
 extern "C" __attribute__((visibility("default"))) int fdb_bcd_sweep(const float *h, const float *host_gram, const float *beta_in, float *beta_out,
                              const int32_t *indptr, const int32_t *indices, int64_t n_rows, int32_t n_types,
                              float lambda, float rho_scaled, float tol, int32_t finalize, void *state,
-                             void *stream)
+                             const void *plan, void *stream)
 {
     int rc = check_solver_args(h, host_gram, beta_in, beta_out, indptr, n_rows, n_types, state);
     if (rc || n_rows == 0) return rc;
     return dispatch_sweep(h, host_gram, n_types, beta_in, beta_out, indptr, indices, n_rows, lambda, rho_scaled,
-                          tol, finalize, (SolveState *)state, (cudaStream_t)stream);
+                          tol, finalize, (SolveState *)state, plan, (cudaStream_t)stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int fdb_bcd_finalize(void *state, float tol, void *stream)
@@ -1001,7 +1097,7 @@ extern "C" __attribute__((visibility("default"))) int fdb_bcd_init(float *beta, 
 extern "C" __attribute__((visibility("default"))) int fdb_bcd_solve(const float *h, const float *host_gram, float *beta_a, float *beta_b,
                              const int32_t *indptr, const int32_t *indices, int64_t n_rows, int32_t n_types,
                              float lambda, float rho_scaled, int32_t max_iter, float tol, void *state,
-                             void *stream)
+                             const void *plan, void *stream)
 {
     int rc = check_solver_args(h, host_gram, beta_a, beta_b, indptr, n_rows, n_types, state);
     if (rc) return rc;
@@ -1011,7 +1107,7 @@ extern "C" __attribute__((visibility("default"))) int fdb_bcd_solve(const float 
     float *cur = beta_a, *nxt = beta_b;
     for (int it = 0; it < max_iter; ++it) {
         rc = dispatch_sweep(h, host_gram, n_types, cur, nxt, indptr, indices, n_rows, lambda, rho_scaled, tol, 1,
-                            (SolveState *)state, (cudaStream_t)stream);
+                            (SolveState *)state, plan, (cudaStream_t)stream);
         if (rc) return rc;
         float *t = cur; cur = nxt; nxt = t;
     }

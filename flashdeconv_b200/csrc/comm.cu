@@ -18,7 +18,8 @@
 
 extern "C" int fdb_bcd_sweep(const float *h, const float *host_gram, const float *beta_in, float *beta_out,
                              const int32_t *indptr, const int32_t *indices, int64_t n_rows, int32_t n_types,
-                             float lambda, float rho_scaled, float tol, int32_t finalize, void *state, void *stream);
+                             float lambda, float rho_scaled, float tol, int32_t finalize, void *state, const void *plan,
+                             void *stream);
 extern "C" int fdb_bcd_finalize(void *state, float tol, void *stream);
 extern "C" int fdb_bcd_init(float *beta, int64_t n_rows, int32_t n_types, void *state, void *stream);
 extern "C" int fdb_rows_gather(const float *src, const int32_t *rows, int64_t n_list, int32_t row_floats, float *dst,
@@ -146,7 +147,7 @@ FDB_API int fdb_bcd_solve_tiled(const float *h, const float *host_gram, float *b
                                 const int64_t *host_recv_first, const int64_t *host_recv_count, int32_t n_send,
                                 const int32_t *host_send_peer, const int32_t *const *host_send_rows,
                                 const int64_t *host_send_count, float *const *host_send_buf, void *comm,
-                                void *stream)
+                                const void *plan, void *stream)
 {
     FDB_REQUIRE(comm != nullptr && state != nullptr, "null communicator / state");
     FDB_REQUIRE(n_own >= 0 && n_total >= n_own && max_iter >= 0, "bad sizes");
@@ -163,7 +164,7 @@ FDB_API int fdb_bcd_solve_tiled(const float *h, const float *host_gram, float *b
     for (int it = 0; it < max_iter; ++it) {
         if (n_own > 0) {
             rc = fdb_bcd_sweep(h, host_gram, cur, nxt, indptr, indices, n_own, n_types, lambda, rho_scaled, tol, 0,
-                               state, stream);
+                               state, plan, stream);
             if (rc) return rc;
         }
         rc = exchange(nxt, n_own, kp, n_recv, host_recv_peer, host_recv_first, host_recv_count, n_send, host_send_peer,

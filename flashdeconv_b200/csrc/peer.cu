@@ -21,7 +21,8 @@
 
 extern "C" int fdb_bcd_sweep(const float *h, const float *host_gram, const float *beta_in, float *beta_out,
                              const int32_t *indptr, const int32_t *indices, int64_t n_rows, int32_t n_types,
-                             float lambda, float rho_scaled, float tol, int32_t finalize, void *state, void *stream);
+                             float lambda, float rho_scaled, float tol, int32_t finalize, void *state, const void *plan,
+                             void *stream);
 extern "C" int fdb_bcd_init(float *beta, int64_t n_rows, int32_t n_types, void *state, void *stream);
 
 namespace fdb {
@@ -109,7 +110,8 @@ FDB_API int fdb_bcd_solve_peer(const float *h, const float *host_gram, void *con
                                int32_t world, int64_t cap_rows, const int32_t *indptr, const int32_t *indices,
                                int64_t n_own, int64_t n_total, int32_t n_types, float lambda, float rho_scaled,
                                int32_t max_iter, float tol, void *state, int64_t n_push, const int32_t *push_src_row,
-                               const int32_t *push_peer, const int64_t *push_dst_row, uint32_t seq_base, void *stream)
+                               const int32_t *push_peer, const int64_t *push_dst_row, uint32_t seq_base,
+                               const void *plan, void *stream)
 {
     FDB_REQUIRE(host_peer_base && state, "null peer table / state");
     FDB_REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world, "world must be in [1, %d]", kMaxRanks);
@@ -134,7 +136,7 @@ FDB_API int fdb_bcd_solve_peer(const float *h, const float *host_gram, void *con
     for (int it = 0; it < max_iter; ++it) {
         if (n_own > 0) {
             rc = fdb_bcd_sweep(h, host_gram, mine + cur, mine + nxt, indptr, indices, n_own, n_types, lambda, rho_scaled,
-                               tol, 0, state, stream);
+                               tol, 0, state, plan, stream);
             if (rc) return rc;
         }
         if (n_push > 0) {

@@ -197,6 +197,19 @@ def build_graph(coords_dev, method="knn", k=6, radius=None) -> DeviceGraph:
     return DeviceGraph(order, rank, indptr, indices, int(nnz.value), rad.value if method != "knn" else None)
 
 
+def build_sweep_plan(indptr, indices, n_rows: int, nnz: int, n_types: int):
+    """Gather plan for the sweep kernel (per-patch halo rows + 16-bit neighbour codes), built once per graph.
+    Returns a uint8 CUDA tensor, or None when this row width needs no plan."""
+    torch = _native.require_cuda()
+    nbytes = int(lib.fdb_bcd_plan_bytes(int(n_rows), int(nnz), int(n_types)))
+    if nbytes == 0:
+        return None
+    plan = torch.empty(nbytes, dtype=torch.uint8, device=indptr.device)
+    check(lib.fdb_bcd_plan_build(_ptr(indptr), _ptr(indices), int(n_rows), int(nnz), int(n_types), _ptr(plan), nbytes,
+                                 _stream(torch)), "bcd_plan_build")
+    return plan
+
+
 @dataclass
 class SolveResult:
     beta: np.ndarray                   # N x K float64, input order
@@ -258,10 +271,11 @@ class DevicePath:
 
     def stage_solve(self, lam: float, rho_scaled: float, max_iter: int, tol: float):
         g = self.graph
+        self.plan = build_sweep_plan(g.indptr, g.indices, self.csr.shape[0], g.nnz, self.K) if max_iter else None
         check(lib.fdb_bcd_solve(_ptr(self.h), self.gram32.ctypes.data_as(C.c_void_p), _ptr(self.beta_a),
                                 _ptr(self.beta_b), _ptr(g.indptr), _ptr(g.indices), self.csr.shape[0], self.K,
                                 float(lam), float(rho_scaled), int(max_iter), float(tol), _ptr(self.state),
-                                _stream(self.torch)), "bcd_solve")
+                                _ptr(self.plan), _stream(self.torch)), "bcd_solve")
 
     def read_state(self):
         st = self.state.cpu()
@@ -361,13 +375,14 @@ class DevicePath:
         """Sweep-at-a-time loop used only for verbose=True (objective every 10 sweeps, core/solver.py:399-404)."""
         g, n = self.graph, self.csr.shape[0]
         st = _stream(self.torch)
+        plan = build_sweep_plan(g.indptr, g.indices, n, g.nnz, self.K)
         check(lib.fdb_bcd_init(_ptr(self.beta_a), n, self.K, _ptr(self.state), st), "bcd_init")
         cur, nxt = self.beta_a, self.beta_b
         n_iter, conv, rel = 0, False, 0.0
         for it in range(max_iter):
             check(lib.fdb_bcd_sweep(_ptr(self.h), self.gram32.ctypes.data_as(C.c_void_p), _ptr(cur), _ptr(nxt),
                                     _ptr(g.indptr), _ptr(g.indices), n, self.K, float(lam), float(rho_s),
-                                    float(tol), 1, _ptr(self.state), st), "bcd_sweep")
+                                    float(tol), 1, _ptr(self.state), _ptr(plan), st), "bcd_sweep")
             n_iter, conv, rel = self.read_state()
             if it % 10 == 0 or it == max_iter - 1:
                 obj = self.objective(nxt, lam, rho_s)

@@ -70,6 +70,8 @@ class _Problem:
         self.a = torch.empty((self.n, self.Kp), dtype=torch.float32, device=dev)
         self.b = torch.empty((self.n, self.Kp), dtype=torch.float32, device=dev)
         self.state = torch.zeros(16, dtype=torch.int32, device=dev)
+        from .pipeline import build_sweep_plan
+        self.plan = build_sweep_plan(self.indptr, self.indices, self.n, Ac.nnz, self.K)
 
     def read_state(self):
         st = self.state.cpu()
@@ -99,7 +101,7 @@ def bcd_solve(Y_sketch: np.ndarray, X_sketch: np.ndarray, A, lambda_: float = 0.
     if not verbose:
         P.check(P.lib.fdb_bcd_solve(P._ptr(P.h), P.gram_ptr, P._ptr(P.a), P._ptr(P.b), P._ptr(P.indptr),
                                     P._ptr(P.indices), n, K, float(lambda_), float(rho_scaled), int(max_iter),
-                                    float(tol), P._ptr(P.state), st), "bcd_solve")
+                                    float(tol), P._ptr(P.state), P._ptr(P.plan), st), "bcd_solve")
         n_iter, conv, rel = P.read_state()
     else:
         P.check(P.lib.fdb_bcd_init(P._ptr(P.a), n, K, P._ptr(P.state), st), "bcd_init")
@@ -108,7 +110,7 @@ def bcd_solve(Y_sketch: np.ndarray, X_sketch: np.ndarray, A, lambda_: float = 0.
         for it in range(max_iter):
             P.check(P.lib.fdb_bcd_sweep(P._ptr(P.h), P.gram_ptr, P._ptr(cur), P._ptr(nxt), P._ptr(P.indptr),
                                         P._ptr(P.indices), n, K, float(lambda_), float(rho_scaled), float(tol), 1,
-                                        P._ptr(P.state), st), "bcd_sweep")
+                                        P._ptr(P.state), P._ptr(P.plan), st), "bcd_sweep")
             n_iter, conv, rel = P.read_state()
             if it % 10 == 0 or it == max_iter - 1:
                 obj = P.objective(nxt, lambda_, rho_scaled)

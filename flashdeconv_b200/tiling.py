@@ -299,6 +299,8 @@ class TiledPath:
         t, p, pl = self.torch, self.plan, self.pl
         st = self._stream()
         gram = self.gram32.ctypes.data_as(C.c_void_p)
+        nnz_local = int(p.indices.numel())
+        self.sweep_plan = pl.build_sweep_plan(p.indptr, p.indices, p.n_own, nnz_local, self.K) if (p.n_own and max_iter) else None
         if self.mode == "peer":
             global _SEQ_BASE
             bases = (C.c_void_p * self.world)(*self.peer_ptrs)
@@ -307,7 +309,8 @@ class TiledPath:
             self.check(self.lib.fdb_bcd_solve_peer(
                 pl._ptr(self.h), gram, bases, self.rank, self.world, self.cap_rows, pl._ptr(p.indptr), pl._ptr(p.indices),
                 p.n_own, p.n_total, self.K, float(lam), float(rho_scaled), int(max_iter), float(tol), pl._ptr(self.state),
-                self.n_push, pl._ptr(self.push_src), pl._ptr(self.push_peer), pl._ptr(self.push_dst), seq, st),
+                self.n_push, pl._ptr(self.push_src), pl._ptr(self.push_peer), pl._ptr(self.push_dst), seq,
+                pl._ptr(self.sweep_plan), st),
                 "bcd_solve_peer")
             return
         if self.comm is not None:
@@ -324,7 +327,7 @@ class TiledPath:
                 pl._ptr(self.h), gram, pl._ptr(self.beta_a), pl._ptr(self.beta_b), pl._ptr(p.indptr), pl._ptr(p.indices),
                 p.n_own, p.n_total, self.K, float(lam), float(rho_scaled), int(max_iter), float(tol),
                 pl._ptr(self.state), nr, recv_peer, recv_first, recv_count, ns, send_peer, send_rows, send_count,
-                send_buf, self.comm, st), "bcd_solve_tiled")
+                send_buf, self.comm, pl._ptr(self.sweep_plan), st), "bcd_solve_tiled")
             return
         self.check(self.lib.fdb_bcd_init(pl._ptr(self.beta_a), p.n_total, self.K, pl._ptr(self.state), st), "bcd_init")
         self.check(self.lib.fdb_bcd_init(pl._ptr(self.beta_b), p.n_total, self.K, pl._ptr(None), st), "bcd_init")
@@ -334,7 +337,8 @@ class TiledPath:
             if p.n_own:
                 self.check(self.lib.fdb_bcd_sweep(pl._ptr(self.h), gram, pl._ptr(cur), pl._ptr(nxt), pl._ptr(p.indptr),
                                                   pl._ptr(p.indices), p.n_own, self.K, float(lam), float(rho_scaled),
-                                                  float(tol), 0, pl._ptr(self.state), st), "bcd_sweep")
+                                                  float(tol), 0, pl._ptr(self.state), pl._ptr(self.sweep_plan), st),
+                           "bcd_sweep")
             self._exchange(nxt)
             self.dist.all_reduce(norms, op=self.dist.ReduceOp.MAX, group=self.group)
             self.check(self.lib.fdb_bcd_finalize(pl._ptr(self.state), float(tol), st), "bcd_finalize")

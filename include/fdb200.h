@@ -135,7 +135,15 @@ int fdb_graph_to_input_order(const int32_t *indptr, const int32_t *indices, cons
 int fdb_bcd_sweep(const float *h, const float *host_gram, const float *beta_in, float *beta_out,
                   const int32_t *indptr, const int32_t *indices, int64_t n_rows, int32_t n_types,
                   float lambda, float rho_scaled, float tol, int32_t finalize, void *state,
-                  void *stream);
+                  const void *plan, void *stream);
+
+/* Gather plan: per-patch halo row lists + 16-bit neighbour codes, built ONCE per graph (the adjacency does not
+ * change between sweeps) into a caller-provided device buffer of fdb_bcd_plan_bytes() bytes (0 = this row width
+ * needs none).  Passing it to the sweep / solve entry points selects the fastest sweep kernel (shared-memory
+ * fp16 gather tile); `plan` may be NULL everywhere (slower fp32 kernel, identical semantics). */
+int64_t fdb_bcd_plan_bytes(int64_t n_rows, int64_t nnz, int32_t n_types);
+int fdb_bcd_plan_build(const int32_t *indptr, const int32_t *indices, int64_t n_rows, int64_t nnz,
+                       int32_t n_types, void *plan, int64_t plan_bytes, void *stream);
 
 /* Single-thread kernel doing the finalize step on an externally reduced state block (the
  * multi-GPU path all-reduces words [0],[1] with MAX between sweep and finalize). */
@@ -150,7 +158,7 @@ int fdb_bcd_init(float *beta, int64_t n_rows, int32_t n_types, void *state, void
 int fdb_bcd_solve(const float *h, const float *host_gram, float *beta_a, float *beta_b,
                   const int32_t *indptr, const int32_t *indices, int64_t n_rows, int32_t n_types,
                   float lambda, float rho_scaled, int32_t max_iter, float tol, void *state,
-                  void *stream);
+                  const void *plan, void *stream);
 
 /* (a10) objective pieces in float64: out[0]=sum(beta*H) out[1]=sum_i b_i^T G b_i
  * out[2]=Tr(b^T L b) out[3]=sum|beta| out[4]=sum ysq.  Replaces compute_objective
@@ -197,7 +205,7 @@ int fdb_bcd_solve_tiled(const float *h, const float *host_gram, float *beta_a, f
                         const int64_t *host_recv_first, const int64_t *host_recv_count, int32_t n_send,
                         const int32_t *host_send_peer, const int32_t *const *host_send_rows,
                         const int64_t *host_send_count, float *const *host_send_buf, void *comm,
-                        void *stream);
+                        const void *plan, void *stream);
 
 /* Peer-memory form of fdb_bcd_solve_tiled: no NCCL on the data path.  Every rank's beta buffers live in a
  * symmetric allocation mapped by all peers; host_peer_base[p] is rank p's base pointer as seen from THIS
@@ -212,7 +220,8 @@ int fdb_bcd_solve_peer(const float *h, const float *host_gram, void *const *host
                        int32_t world, int64_t cap_rows, const int32_t *indptr, const int32_t *indices,
                        int64_t n_own, int64_t n_total, int32_t n_types, float lambda, float rho_scaled,
                        int32_t max_iter, float tol, void *state, int64_t n_push, const int32_t *push_src_row,
-                       const int32_t *push_peer, const int64_t *push_dst_row, uint32_t seq_base, void *stream);
+                       const int32_t *push_peer, const int64_t *push_dst_row, uint32_t seq_base,
+                       const void *plan, void *stream);
 
 /* Multi-GPU helpers: gather / scatter whole beta rows by index list (halo exchange staging). */
 int fdb_rows_gather(const float *src, const int32_t *rows, int64_t n_list, int32_t row_floats,
