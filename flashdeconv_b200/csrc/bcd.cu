@@ -357,6 +357,8 @@ bcd_plan_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ 
         codes[j] = code;
     }
     if (threadIdx.x == 0) halo_cnt[blockIdx.x] = min(count, HCAP);
+    // unused slots carry -1 so that the sweep kernel can fetch the list without knowing its length first
+    if ((int)threadIdx.x >= count) halo_rows[(int64_t)blockIdx.x * HCAP + threadIdx.x] = -1;
 }
 
 template <int KP, int NW, int MINB>
@@ -390,7 +392,7 @@ bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
     const int my_row = tile_base + wrow + lane;
     int my_s = 0, my_e = 0;
     if (my_row < n_rows) { my_s = __ldg(indptr + my_row); my_e = __ldg(indptr + my_row + 1); }
-    const int n_halo = __ldg(plan.halo_cnt + blockIdx.x);
+    const int halo_id = __ldg(plan.halo_rows + (size_t)blockIdx.x * HCAP + threadIdx.x);   // slot = thread, -1 = unused
     auto to_gather = [&](int grow, int q, const float4 bb) {
         const __half2 lo = __floats2half2_rn(bb.x, bb.y), hi = __floats2half2_rn(bb.z, bb.w);
         uint2 pk;
@@ -408,10 +410,14 @@ bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
         st4(c_tile + L::at(wrow + lr, q), bb);
         to_gather(wrow + lr, q, bb);
     }
-    for (int idx = threadIdx.x; idx < n_halo * Q; idx += TILE) {
-        const int slot = idx / Q, q = idx - slot * Q;
-        const int g = __ldg(plan.halo_rows + (size_t)blockIdx.x * HCAP + slot);
-        to_gather(TILE + slot, q, ld4(beta_in + (size_t)g * KP + 4 * q));
+    // halo rows of this warp's 32 slots: the row ids travel by shuffle, so the row loads depend on one earlier
+    // load only (no shared-memory hand-off, no extra barrier)
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+        const int idx = lane + 32 * i;
+        const int lr = idx / Q, q = idx - lr * Q;
+        const int g = __shfl_sync(kFull, halo_id, lr);
+        if (g >= 0) to_gather(TILE + wrow + lr, q, ld4(beta_in + (size_t)g * KP + 4 * q));
     }
     const int my_deg = my_e - my_s;
     const int ibase = __shfl_sync(kFull, my_s, 0);
