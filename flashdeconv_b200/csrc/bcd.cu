@@ -846,29 +846,31 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
         mean_diag /= (float)n_types;
         const bool weak_coupling = lam * 8.f <= 0.02f * mean_diag;
         if (plan != nullptr && ((variant == 0 && weak_coupling) || variant == 4 || variant == 6)) {   // halo-staged fp16 gather tile
-            // patch size / residency by row width: 73 KB (Kp <= 32), 95 KB (Kp = 40), 55-72 KB at 128 spots (Kp >= 48)
+            // patch size / residency by row width: 68 KB (Kp <= 32), 90 KB (Kp = 40), 50-66 KB at 128 spots (Kp >= 48)
             constexpr int NWH = KP <= 40 ? 8 : 4;
             constexpr int MINB = KP <= 32 ? 3 : (KP <= 40 ? 2 : 3);
-            constexpr int TILE = NWH * 32;
-            const size_t smem = (size_t)TILE * TileLayout<KP>::S * 4 + (size_t)2 * TILE * (KP / 2) * 4 +
-                                (size_t)NWH * kIdxCap * 2;
-            const int64_t n_ctas = ceil_div(n_rows, TILE);
-            const char *pbase = (const char *)plan;
-            PlanView pv;
-            pv.halo_cnt = (const int32_t *)(pbase + plan_off_cnt());
-            pv.halo_rows = (const int32_t *)(pbase + plan_off_rows(n_ctas));
-            pv.codes = (const uint16_t *)(pbase + plan_off_codes(n_ctas, TILE));
-            auto run = [&](auto kern) -> int {
+            auto run = [&](auto kern, int nw) -> int {
+                const int tile = nw * 32;
+                const size_t smem = (size_t)tile * TileLayout<KP>::S * 4 + (size_t)2 * tile * (KP / 2) * 4 +
+                                    (size_t)nw * kIdxCap * 2;
+                const int64_t n_ctas = ceil_div(n_rows, tile);
+                const char *pbase = (const char *)plan;
+                PlanView pv;
+                pv.halo_cnt = (const int32_t *)(pbase + plan_off_cnt());
+                pv.halo_rows = (const int32_t *)(pbase + plan_off_rows(n_ctas));
+                pv.codes = (const uint16_t *)(pbase + plan_off_codes(n_ctas, tile));
                 FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                kern<<<(int)n_ctas, TILE, smem, st>>>(h, G, beta_in, beta_out, indptr, indices, pv, (int)n_rows,
+                kern<<<(int)n_ctas, tile, smem, st>>>(h, G, beta_in, beta_out, indptr, indices, pv, (int)n_rows,
                                                       n_types, lam, rho, tol, finalize, state);
                 FDB_LAUNCH_CHECK("bcd_sweep_h_kernel");
                 return FDB_OK;
             };
             if constexpr (KP <= 32) {
-                if (variant == 6) return run(bcd_sweep_h_kernel<KP, NWH, 2>);   // tuning: 2 CTAs/SM, 126 registers
+                if (variant == 6) return run(bcd_sweep_h_kernel<KP, NWH, 2>, NWH);   // tuning: 2 CTAs/SM, 126 registers
+                static const bool small = getenv("FDB_SWEEP_TILE128") != nullptr;
+                if (small) return run(bcd_sweep_h_kernel<KP, 4, 6>, 4);              // tuning: 128-spot patches, 6 CTAs/SM
             }
-            return run(bcd_sweep_h_kernel<KP, NWH, MINB>);
+            return run(bcd_sweep_h_kernel<KP, NWH, MINB>, NWH);
         }
     }
     if constexpr (KP <= 32) {
@@ -1036,7 +1038,8 @@ static int plan_tile_rows(int n_types)
 {
     const int kp = fdb_padded_types(n_types);
     if (kp % 8 != 0) return 0;                         // no half gather tile for this row width: no plan needed
-    return kp <= 40 ? 256 : 128;                       // must match the dispatcher in launch_sweep
+    static const bool small = getenv("FDB_SWEEP_TILE128") != nullptr;      // tuning switch
+    return (kp <= 40 && !small) ? 256 : 128;           // must match the dispatcher in launch_sweep
 }
 
 extern "C" __attribute__((visibility("default"))) int64_t fdb_bcd_plan_bytes(int64_t n_rows, int64_t nnz, int32_t n_types)
