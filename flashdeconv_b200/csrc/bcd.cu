@@ -366,7 +366,8 @@ __global__ void __launch_bounds__(NW * 32, MINB)
 bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP> G,
                    const float *__restrict__ beta_in, float *__restrict__ beta_out,
                    const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, PlanView plan,
-                   int n_rows, int n_types, float lam, float rho, float tol, int finalize, SolveState *state)
+                   int n_rows, int n_types, float lam, float rho, float tol, int finalize, SolveState *state,
+                   int pf_stride)
 {
     static_assert(KP % 8 == 0, "half gather rows need Kp % 8 == 0");
     const int already_converged = *reinterpret_cast<volatile int *>(&state->converged);
@@ -425,6 +426,15 @@ bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
     const bool staged = icnt <= kIdxCap;
     if (staged)
         for (int t = lane; t < icnt; t += 32) iw[t] = plan.codes[ibase + t];
+    // pull the rows of the patch that runs on this SM slot one wave from now into L2 (one 128-byte line of
+    // beta_old and one of H per thread), so its start-of-CTA loads are L2 hits instead of DRAM round trips
+    if (pf_stride > 0) {
+        const int64_t prow = (int64_t)(blockIdx.x + pf_stride) * TILE + threadIdx.x;
+        if (prow < n_rows) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(beta_in + prow * KP));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(h + prow * KP));
+        }
+    }
     __syncthreads();                                     // tiles, halo rows and code slices are in shared memory
     if (already_converged) return;                       // uniform across the grid
 
@@ -845,10 +855,11 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
         for (int k = 0; k < n_types; ++k) mean_diag += host_gram[k * n_types + k];
         mean_diag /= (float)n_types;
         const bool weak_coupling = lam * 8.f <= 0.02f * mean_diag;
-        if (plan != nullptr && ((variant == 0 && weak_coupling) || variant == 4 || variant == 6)) {   // halo-staged fp16 gather tile
-            // patch size / residency by row width: 68 KB (Kp <= 32), 90 KB (Kp = 40), 50-66 KB at 128 spots (Kp >= 48)
-            constexpr int NWH = KP <= 40 ? 8 : 4;
-            constexpr int MINB = KP <= 32 ? 3 : (KP <= 40 ? 2 : 3);
+        if (plan != nullptr && ((variant == 0 && weak_coupling) || variant == 4)) {   // halo-staged fp16 gather tile
+            // 128-spot patches (4 warps); residency by row width: 6 CTAs/SM at 34 KB (Kp <= 32), 4 at 45 KB (Kp = 40),
+            // 3 at 50-66 KB (Kp >= 48).  FDB_SWEEP_TILE256 selects 256-spot patches (3 % slower at C3, 6 % less traffic)
+            constexpr int NWH = 4;
+            constexpr int MINB = KP <= 32 ? 6 : 3;
             auto run = [&](auto kern, int nw) -> int {
                 const int tile = nw * 32;
                 const size_t smem = (size_t)tile * TileLayout<KP>::S * 4 + (size_t)2 * tile * (KP / 2) * 4 +
@@ -860,15 +871,18 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
                 pv.halo_rows = (const int32_t *)(pbase + plan_off_rows(n_ctas));
                 pv.codes = (const uint16_t *)(pbase + plan_off_codes(n_ctas, tile));
                 FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                static const int pf_env = getenv("FDB_SWEEP_PREFETCH") ? atoi(getenv("FDB_SWEEP_PREFETCH")) : -1;
+                int resident = 0;
+                FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, tile, smem));
+                const int pf_stride = pf_env >= 0 ? pf_env : kNumSM * std::max(resident, 1) / 2;   // half a wave ahead
                 kern<<<(int)n_ctas, tile, smem, st>>>(h, G, beta_in, beta_out, indptr, indices, pv, (int)n_rows,
-                                                      n_types, lam, rho, tol, finalize, state);
+                                                      n_types, lam, rho, tol, finalize, state, pf_stride);
                 FDB_LAUNCH_CHECK("bcd_sweep_h_kernel");
                 return FDB_OK;
             };
             if constexpr (KP <= 32) {
-                if (variant == 6) return run(bcd_sweep_h_kernel<KP, NWH, 2>, NWH);   // tuning: 2 CTAs/SM, 126 registers
-                static const bool small = getenv("FDB_SWEEP_TILE128") != nullptr;
-                if (small) return run(bcd_sweep_h_kernel<KP, 4, 6>, 4);              // tuning: 128-spot patches, 6 CTAs/SM
+                static const bool big = getenv("FDB_SWEEP_TILE256") != nullptr;
+                if (big) return run(bcd_sweep_h_kernel<KP, 8, 3>, 8);                // tuning: 256-spot patches, 3 CTAs/SM
             }
             return run(bcd_sweep_h_kernel<KP, NWH, MINB>, NWH);
         }
@@ -1038,8 +1052,8 @@ static int plan_tile_rows(int n_types)
 {
     const int kp = fdb_padded_types(n_types);
     if (kp % 8 != 0) return 0;                         // no half gather tile for this row width: no plan needed
-    static const bool small = getenv("FDB_SWEEP_TILE128") != nullptr;      // tuning switch
-    return (kp <= 40 && !small) ? 256 : 128;           // must match the dispatcher in launch_sweep
+    static const bool big = getenv("FDB_SWEEP_TILE256") != nullptr;        // tuning switch
+    return (kp <= 32 && big) ? 256 : 128;              // must match the dispatcher in launch_sweep
 }
 
 extern "C" __attribute__((visibility("default"))) int64_t fdb_bcd_plan_bytes(int64_t n_rows, int64_t nnz, int32_t n_types)
