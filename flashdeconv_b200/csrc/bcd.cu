@@ -73,6 +73,14 @@ __device__ __forceinline__ float rcp_fast(float x)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ float2 fmul2(const float2 a, const float2 b)
+{
+    unsigned long long ua = *reinterpret_cast<const unsigned long long *>(&a);
+    unsigned long long ub = *reinterpret_cast<const unsigned long long *>(&b);
+    unsigned long long ud;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(ud) : "l"(ua), "l"(ub));
+    return *reinterpret_cast<float2 *>(&ud);
+}
 __device__ __forceinline__ float elem(const float4 &v, int j) { return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w; }
 __device__ __forceinline__ void set_elem(float4 &v, int j, float x)
 {
@@ -530,7 +538,8 @@ bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
                 const float part = (a0.x + a0.y) + (a1.x + a1.y);
                 const float old = (k & 1) ? b2[k / 2].y : b2[k / 2].x;
                 const float den = G.diag[k] + lam_deg;
-                const float nv = den > 1e-10f ? fmaxf(0.f, __fdividef(part - rho, den)) : 0.f;
+                // rcp.approx (1 ulp-class, den is far from denormal) and a select instead of a branch
+                const float nv = den > 1e-10f ? fmaxf(0.f, (part - rho) * rcp_fast(den)) : 0.f;
                 dmax = fmaxf(dmax, fabsf(nv - old));
                 amax = fmaxf(amax, fabsf(old));
                 if (k & 1) b2[k / 2].y = nv; else b2[k / 2].x = nv;
