@@ -828,7 +828,7 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
     for (int k = 0; k < n_types; ++k)
         for (int a = 0; a < n_types; ++a) G.g[k * KP + a] = (a == k) ? 0.f : -host_gram[k * n_types + a];
     static const bool use_ws = getenv("FDB_SWEEP_WS") != nullptr;
-    if (use_ws) {
+    if constexpr (KP == 32) if (use_ws) {          // comparison kernel, built for Kp = 32 only
         using L = WsLayout<KP>;
         static int ctas_per_sm = 0;
         if (!ctas_per_sm) {
@@ -898,8 +898,6 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
     }
     if constexpr (KP <= 32) {
         if (variant == 1) return go(bcd_sweep_kernel<KP, 4, 1>, 4);
-        if (variant == 2) return go(bcd_sweep_kernel<KP, 8, 2>, 8);
-        if (variant == 3) return go(bcd_sweep_kernel<KP, 4, 2>, 4);
         return go(bcd_sweep_kernel<KP, 8, 1>, 8);        // variant 5 (or Kp % 8 != 0): fp32 gather, no halo staging
     } else {
         return go(bcd_sweep_kernel<KP, 4, 1>, 4);

@@ -368,28 +368,31 @@ def test_fit_variants_behave_like_the_reference_tests():
         FlashDeconv(preprocess="pearson").fit(Yd, ds.X, ds.coords)
 
 
-# ---------------------------------------------------------------- multi-GPU tiling (NCCL)
-def _run_tiled(nproc):
+# ---------------------------------------------------------------- multi-GPU tiling
+def _run_tiled(nproc, mode):
     import os, subprocess, sys
     from conftest import ROOT
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(29500 + 7 * nproc + os.getpid() % 400),
            os.path.join(ROOT, "tools", "check_tiled.py"), "20000"]
-    return subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, FDB_TILED_MODE=mode))
 
 
-def test_tiled_path_single_rank_equals_device_path():
-    out = _run_tiled(1)
+@pytest.mark.parametrize("mode", ["peer", "nccl", "torch"])
+def test_tiled_path_single_rank_equals_device_path(mode):
+    out = _run_tiled(1, mode)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
 
 
-def test_tiled_path_two_ranks_equals_device_path():
+@pytest.mark.parametrize("mode", ["peer", "nccl", "torch"])
+def test_tiled_path_two_ranks_equals_device_path(mode):
+    """spatial tiles + halo exchange reproduce the single-GPU result bit for bit (needs 2 GPUs)"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    out = _run_tiled(2)
+    out = _run_tiled(2, mode)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "OK" in out.stdout
+    assert "OK" in out.stdout and f"[{mode}]" in out.stdout
 
 
 # ---------------------------------------------------------------- f1: gene moments on the device
