@@ -23,6 +23,7 @@
 //   phase C (coalesced): the warp streams its 32 new rows back out.
 //   Convergence statistics: redux.sync max per warp, one atomicMax per CTA, last CTA finalises.
 #include <algorithm>
+#include <type_traits>
 #include <cuda_fp16.h>
 #include <stdlib.h>
 #include "fdb_common.cuh"
@@ -55,17 +56,22 @@ __device__ __forceinline__ void ffma2(float2 &d, const float2 a, const float2 b)
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pack2(float lo, float hi)
 {
-    u64 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
+    return (u64)__float_as_uint(lo) | ((u64)__float_as_uint(hi) << 32);      // folds to mov.b64 {lo, hi}
 }
 __device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi)
 {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    lo = __uint_as_float((unsigned)v);
+    hi = __uint_as_float((unsigned)(v >> 32));
 }
 __device__ __forceinline__ void ffma2q(u64 &d, const u64 a, const u64 b)
 {
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ u64 add2q(const u64 a, const u64 b)
+{
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
 }
 __device__ __forceinline__ float rcp_fast(float x)
 {
@@ -80,6 +86,15 @@ __device__ __forceinline__ float2 fmul2(const float2 a, const float2 b)
     unsigned long long ud;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(ud) : "l"(ua), "l"(ub));
     return *reinterpret_cast<float2 *>(&ud);
+}
+// compile-time loop: f(integral_constant<int, I>) for I in [I0, N)
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
 }
 __device__ __forceinline__ float elem(const float4 &v, int j) { return j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w; }
 __device__ __forceinline__ void set_elem(float4 &v, int j, float x)
@@ -514,39 +529,60 @@ bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
     asm volatile("cp.async.wait_all;");
     __syncwarp();                                        // the warp's H rows have landed in its fp32 tile rows
 
-    // ---------------- step 3: cyclic coordinate descent, direct form on packed FFMA2 (see bcd_sweep_kernel)
+    // ---------------- step 3: cyclic coordinate descent, direct form on packed FFMA2
+    //   part_k = c_k - rho - sum_{j != k} G_kj b_j  (b_j already updated for j < k),  b_k <- max(0, part_k / den_k)
+    // beta lives in 64-bit register pairs, so every FFMA2 takes its beta operand as is.  The two accumulation
+    // chains of step k walk the pairs from the least to the most recently updated one (a rotation starting
+    // right behind beta_k), so only the last link of each chain waits for step k-1: the serial path per step is
+    // FFMA2 -> ADD2 -> FADD -> FMUL -> FMNMX and the other Kp/2-2 FFMA2 of the step fill those latency slots.
+    // (The select on the reciprocal also keeps cicc's compile time sane: without it NVVM spends > 10 min on Kp = 64.)
     float dmax = 0.f, amax = 0.f;
     {
+        constexpr int NP = KP / 2;
         const int trow = wrow + lane;
         const float lam_deg = lam * (float)my_deg;
+        const float neg_rho = -rho;
+        u64 bq[NP];
 #pragma unroll
-        for (int q = 0; q < Q; ++q) {
+        for (int p = 0; p < NP; ++p) {
+            amax = fmaxf(amax, fmaxf(fabsf(b2[p].x), fabsf(b2[p].y)));
+            bq[p] = pack2(b2[p].x, b2[p].y);
+        }
+        static_for<0, Q>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
             const float4 c4 = ld4(c_tile + L::at(trow, q));
             const float2 s01 = __half22float2(acc[2 * q]), s23 = __half22float2(acc[2 * q + 1]);
             const float4 ns4 = make_float4(s01.x, s01.y, s23.x, s23.y);
             float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int k = 4 * q + j;
-                if (k >= KP - 3 && k >= n_types) continue;
-                float2 a0 = make_float2(fmaf(lam, elem(ns4, j), elem(c4, j)), 0.f), a1 = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int jj = 0; jj < KP / 2; ++jj) {
-                    const float2 g = make_float2(G.g[k * KP + 2 * jj], G.g[k * KP + 2 * jj + 1]);
-                    if (jj & 1) ffma2(a1, g, b2[jj]); else ffma2(a0, g, b2[jj]);
-                }
-                const float part = (a0.x + a0.y) + (a1.x + a1.y);
-                const float old = (k & 1) ? b2[k / 2].y : b2[k / 2].x;
+            static_for<0, 4>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                constexpr int k = 4 * q + j;
+                if (k >= KP - 7 && k >= n_types) return;            // padding columns stay zero (warp-uniform)
                 const float den = G.diag[k] + lam_deg;
-                // rcp.approx (1 ulp-class, den is far from denormal) and a select instead of a branch
-                const float nv = den > 1e-10f ? fmaxf(0.f, (part - rho) * rcp_fast(den)) : 0.f;
-                dmax = fmaxf(dmax, fabsf(nv - old));
-                amax = fmaxf(amax, fabsf(old));
-                if (k & 1) b2[k / 2].y = nv; else b2[k / 2].x = nv;
+                const float rinv = den > 1e-10f ? rcp_fast(den) : 0.f;   // core/solver.py:87-90: denominator <= 1e-10 -> 0
+                u64 a0 = pack2(fmaf(lam, elem(ns4, j), elem(c4, j)), neg_rho), a1 = 0ull;
+                constexpr int start = (k + 1) >> 1;
+                static_for<0, NP>([&](auto ic) {
+                    constexpr int i = decltype(ic)::value;
+                    constexpr int jj = (start + i) % NP;
+                    const u64 g = pack2(G.g[k * KP + 2 * jj], G.g[k * KP + 2 * jj + 1]);
+                    if constexpr (i & 1) ffma2q(a1, g, bq[jj]); else ffma2q(a0, g, bq[jj]);
+                });
+                float lo, hi, s0, s1;
+                unpack2(add2q(a0, a1), s0, s1);
+                const float nv = fmaxf(0.f, (s0 + s1) * rinv);
+                unpack2(bq[k >> 1], lo, hi);
+                if constexpr (k & 1) {
+                    dmax = fmaxf(dmax, fabsf(nv - hi));
+                    bq[k >> 1] = pack2(lo, nv);
+                } else {
+                    dmax = fmaxf(dmax, fabsf(nv - lo));
+                    bq[k >> 1] = pack2(nv, hi);
+                }
                 set_elem(n4, j, nv);
-            }
+            });
             st4(c_tile + L::at(trow, q), n4);
-        }
+        });
         if (my_row >= n_rows) { dmax = 0.f; amax = 0.f; }
     }
     __syncwarp();
@@ -581,210 +617,267 @@ bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
 }
 
 // ------------------------------------------------------------------------------------
-// Sweep kernel, warp-specialised persistent form (production).
+// Sweep kernel, persistent software-pipelined form (production for Kp % 8 == 0).
 //
-// The gather of neighbour rows is latency-bound and the coordinate descent is issue-bound; run as
-// consecutive phases of one warp they serialise (CTAs of a wave even fall into lock-step).  Here a
-// CTA is 4 producer warps + 4 consumer warps; producer i streams rows for 32-spot tiles into one of
-// two shared-memory stages and hands them to consumer i through mbarriers, so the SM always has row
-// loads in flight while the FMA pipe runs the descent of earlier tiles.  Tiles are strided over all
-// producer/consumer pairs of a persistent grid (a few CTAs per SM).
+// bcd_sweep_h_kernel runs one patch per CTA, and because every CTA of a wave takes the same time the waves stay
+// in lock-step: all resident CTAs wait on their start-of-patch DRAM round trips together (37 % of the warp time
+// in the round-1 profile), then all compute together while HBM idles.  Here a CTA is persistent and walks
+// patches blockIdx.x, blockIdx.x + gridDim.x, ...; everything patch p+1 needs is requested while patch p is
+// being computed, with no extra shared memory for rows (residency stays at 6 CTAs/SM for Kp <= 32):
+//   * row pointers and halo row ids of p+1: plain loads into registers, consumed one iteration later;
+//   * neighbour codes of p+1: one 16-byte cp.async per lane into the alternate code buffer (after the gather of
+//     p, when the row pointers have landed);
+//   * beta_old rows, H rows and halo rows of p+1: prefetch.global.L2, so that the loads at the start of p+1 are
+//     L2 hits (the prefetched-ahead footprint of the whole grid is ~32 MB of the 126 MB L2);
+//   * H rows of p: cp.async into c_tile once the lane has its own beta_old row in registers, consumed after
+//     the gather; c_tile then receives beta_new and is streamed out.
+// Per patch: two CTA barriers (gather tile free / gather tile complete); statistics stay in registers until
+// the CTA has finished all its patches.
 // ------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+template <int KP, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
+bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP> G,
+                   const float *__restrict__ beta_in, float *__restrict__ beta_out,
+                   const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, PlanView plan,
+                   int n_rows, int n_types, float lam, float rho, float tol, int finalize, SolveState *state,
+                   int n_patches)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    uint32_t done;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                     "selp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
+    static_assert(KP % 8 == 0, "half gather rows need Kp % 8 == 0");
+    using L = TileLayout<KP>;
+    constexpr int Q = L::Q, S = L::S, TILE = NW * 32, HCAP = TILE;
+    constexpr int GQ = Q / 2;                            // 16-byte chunks per fp16 gather row
+    constexpr int GROW = KP / 2;                         // 32-bit words per gather row
+    constexpr int NP = KP / 2;
+    extern __shared__ __align__(16) float sweep_smem[];
+    float *c_tile = sweep_smem;                                                   // TILE x S fp32: beta_old, H, beta_new
+    uint32_t *g_tile = reinterpret_cast<uint32_t *>(c_tile + TILE * S);           // (TILE + HCAP) x GROW words
+    uint16_t *idx_tile = reinterpret_cast<uint16_t *>(g_tile + (TILE + HCAP) * GROW);   // NW x kIdxCap codes
+    int *scal = reinterpret_cast<int *>(idx_tile + NW * kIdxCap);                 // 3 x TILE: row start, end, halo id
+    __shared__ unsigned red[2][NW];
 
-constexpr int kWsPairs = 4;                       // producer/consumer pairs per CTA
-constexpr int kWsThreads = kWsPairs * 64;
-constexpr int kWsIdxCap = 384;                    // staged neighbour indices per tile
-
-template <int KP>
-struct WsLayout {
-    static constexpr int Q = KP / 4;
-    static constexpr bool SWZ = (Q % 8 == 0);                             // XOR swizzle instead of padding
-    static constexpr int S = SWZ ? KP : ((Q % 2 == 1) ? KP : KP + 4);     // floats per staged row
-    static constexpr int kStageFloats = 2 * 32 * S + 32;                  // c tile, b tile, degrees
-    static constexpr int kPairFloats = 2 * kStageFloats + kWsIdxCap;
-    static constexpr size_t kSmemBytes = (size_t)kWsPairs * kPairFloats * 4 + 64;
-    __device__ static __forceinline__ int at(int row, int q)              // float offset of chunk q of a row
-    {
-        return SWZ ? row * S + 4 * (q ^ (row & 7)) : row * S + 4 * q;
-    }
-};
-
-template <int KP>
-__global__ void __launch_bounds__(kWsThreads)
-bcd_sweep_ws_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP> G,
-                    const float *__restrict__ beta_in, float *__restrict__ beta_out,
-                    const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
-                    int n_rows, int n_types, float lam, float rho, float tol, int finalize, SolveState *state)
-{
-    if (*reinterpret_cast<volatile int *>(&state->converged)) return;
-    using L = WsLayout<KP>;
-    constexpr int Q = L::Q, SLOTS = 32 / Q, ITERS = (32 + SLOTS - 1) / SLOTS;
-
-    extern __shared__ __align__(16) float ws_smem[];
-    __shared__ __align__(8) uint64_t bars[kWsPairs][2][2];               // [pair][stage][0 = full, 1 = empty]
-    __shared__ unsigned red[2][kWsPairs];
+    if (*reinterpret_cast<volatile int *>(&state->converged)) return;      // uniform across the grid
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool producer = warp < kWsPairs;
-    const int pair = producer ? warp : warp - kWsPairs;
-    float *pair_smem = ws_smem + (size_t)pair * L::kPairFloats;
-    int *iw = reinterpret_cast<int *>(pair_smem + 2 * L::kStageFloats);
+    const int wrow = warp * 32;
+    const int own = wrow + lane;
+    uint16_t *iw = idx_tile + warp * kIdxCap;
 
-    if (threadIdx.x < kWsPairs * 4) mbar_init(&bars[0][0][0] + threadIdx.x, 1);
-    __syncthreads();
+    // asynchronous copy of the warp's 32 rows of `src` (patch `pp`) into c_tile
+    auto rows_async = [&](const float *__restrict__ src, int pp) {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+            const int idx = lane + 32 * i;
+            const int lr = idx / Q, q = idx - lr * Q;
+            const int p = pp * TILE + wrow + lr;
+            const uint32_t d = (uint32_t)__cvta_generic_to_shared(c_tile + L::at(wrow + lr, q));
+            const int nbytes = p < n_rows ? 16 : 0;                               // rows past the end: zero fill
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d),
+                         "l"(src + (size_t)min(p, n_rows - 1) * KP + 4 * q), "r"(nbytes));
+        }
+    };
+    // this thread's row pointers and halo row id of patch `pp` -> its three private words of `scal`
+    // (asynchronously: nothing is held in registers while the current patch is computed)
+    auto scalars_async = [&](int pp) {
+        const int r = pp * TILE + own;
+        const int nb = r < n_rows ? 4 : 0;
+        const int32_t *src = indptr + min(r, n_rows - 1);
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(scal + threadIdx.x);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(nb));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + 4 * TILE), "l"(src + 1), "r"(nb));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 8 * TILE),
+                     "l"(plan.halo_rows + (size_t)pp * HCAP + threadIdx.x));    // slot = thread, -1 = unused
+    };
 
-    const int n_tiles = (n_rows + 31) / 32;
-    const int pair_global = blockIdx.x * kWsPairs + pair;
-    const int pair_stride = gridDim.x * kWsPairs;
+    // ---------------- prologue: the first patch's scalars
+    int patch = blockIdx.x;
+    scalars_async(patch);
+    asm volatile("cp.async.commit_group;");
+    asm volatile("cp.async.wait_all;");
+
     float dmax = 0.f, amax = 0.f;
+#pragma unroll 1
+    for (; patch < n_patches; patch += gridDim.x) {
+        const int tile_base = patch * TILE;
+        const int next = patch + gridDim.x;
+        const int my_row = tile_base + own;
+        const int my_s = scal[threadIdx.x], my_e = scal[TILE + threadIdx.x];
+        const int halo_id = scal[2 * TILE + threadIdx.x];
+        const int my_deg = my_e - my_s;
+        // the warp's slice of neighbour codes, staged from the 8-element-aligned position below its first entry
+        const int ibase = __shfl_sync(kFull, my_s, 0) & ~7;
+        const int icnt = __reduce_max_sync(kFull, my_e) - ibase;
+        const bool staged = icnt <= kIdxCap;
+        if (staged && 8 * lane < icnt) {
+            const uint32_t d = (uint32_t)__cvta_generic_to_shared(iw + 8 * lane);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(plan.codes + ibase + 8 * lane));
+        }
+        // the warp's beta_old rows -> c_tile (its rows of c_tile were streamed out at the end of the previous patch)
+        rows_async(beta_in, patch);
+        asm volatile("cp.async.commit_group;");
+        // the patch's halo rows (ids travel by shuffle); like everything above these are L2 hits: the lines were
+        // prefetched while the previous patch was computed
+        float4 hrow[Q];
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+            const int idx = lane + 32 * i;
+            const int lr = idx / Q, q = idx - lr * Q;
+            const int g = __shfl_sync(kFull, halo_id, lr);
+            hrow[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g >= 0) hrow[i] = ld4(beta_in + (size_t)g * KP + 4 * q);
+        }
+        asm volatile("cp.async.wait_all;");
+        __syncthreads();                 // (1) every warp is past the gather of the previous patch: g_tile is free
+        auto to_gather = [&](int grow, int q, const float4 bb) {
+            const __half2 lo = __floats2half2_rn(bb.x, bb.y), hi = __floats2half2_rn(bb.z, bb.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t *>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t *>(&hi);
+            *reinterpret_cast<uint2 *>(g_tile + grow * GROW + 4 * ((q >> 1) ^ gsw<GQ>(grow)) + 2 * (q & 1)) = pk;
+        };
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+            const int idx = lane + 32 * i;
+            const int lr = idx / Q, q = idx - lr * Q;
+            to_gather(TILE + wrow + lr, q, hrow[i]);
+            to_gather(wrow + lr, q, ld4(c_tile + L::at(wrow + lr, q)));
+        }
+        // own beta_old row -> registers (fp32)
+        u64 bq[NP];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const float4 b4 = ld4(c_tile + L::at(own, q));
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(b4.x), fabsf(b4.y)), fmaxf(fabsf(b4.z), fabsf(b4.w))));
+            bq[2 * q] = pack2(b4.x, b4.y);
+            bq[2 * q + 1] = pack2(b4.z, b4.w);
+        }
+        __syncthreads();                 // (2) gather tile complete; the warp's fp32 rows are consumed
 
-    if (producer) {
-        // ================= producer: stream rows, leave c = H + lam * sum_j beta_old[j] and beta_old in a stage
-        const int slot = lane / Q, q = lane - slot * Q;
-        int n = 0;
-        for (int tile = pair_global; tile < n_tiles; tile += pair_stride, ++n) {
-            const int st = n & 1;
-            float *cw = pair_smem + st * L::kStageFloats;
-            float *bw = cw + 32 * L::S;
-            int *dw = reinterpret_cast<int *>(bw + 32 * L::S);
-            const int wbase = tile * 32;
-            const int my_row = wbase + lane;
-            int my_s = 0, my_e = 0;
-            if (my_row < n_rows) { my_s = __ldg(indptr + my_row); my_e = __ldg(indptr + my_row + 1); }
-            const int my_deg = my_e - my_s;
-            const int ibase = __shfl_sync(kFull, my_s, 0);
-            const int icnt = __reduce_max_sync(kFull, my_e - ibase);
-            const bool staged = icnt <= kWsIdxCap;
-            // the stage (and the index buffer, which the previous tile's gathers no longer need) must be free
-            mbar_wait(&bars[pair][st][1], ((n >> 1) & 1) ^ 1);
-            if (staged)
-                for (int t = lane; t < icnt; t += 32) iw[t] = __ldg(indices + ibase + t);
-            dw[lane] = my_deg;
-            __syncwarp();
-#pragma unroll 2
-            for (int it = 0; it < ITERS; ++it) {
-                const int lr = it * SLOTS + slot;
-                const int src = lr < 32 ? lr : 31;
-                const int rs = __shfl_sync(kFull, my_s, src) - ibase;
-                const int deg = __shfl_sync(kFull, my_deg, src);
-                const bool active = slot < SLOTS && lr < 32;
-                const int p = wbase + lr;
-                const bool live = active && p < n_rows;
-                const int trip = __reduce_max_sync(kFull, live ? deg : 0);
-                float4 own = make_float4(0.f, 0.f, 0.f, 0.f), cc = own, acc = own;
-                const int pc = live ? p : 0;                                   // clamp: loads stay in bounds
-                if (live) {
-                    own = ld4(beta_in + (size_t)pc * KP + 4 * q);
-                    cc = __ldcs(reinterpret_cast<const float4 *>(h + (size_t)pc * KP + 4 * q));
-                }
-#pragma unroll 4
-                for (int u = 0; u < trip; ++u) {
-                    // absent neighbours read the spot's own (cache-hot) row with weight 0: no branches
-                    const bool has = live && u < deg;
-                    int nb = pc;
-                    if (has) nb = staged ? iw[rs + u] : __ldg(indices + ibase + rs + u);
-                    const float4 v = ld4(beta_in + (size_t)nb * KP + 4 * q);
-                    const float m = has ? 1.f : 0.f;
-                    acc.x = fmaf(v.x, m, acc.x); acc.y = fmaf(v.y, m, acc.y);
-                    acc.z = fmaf(v.z, m, acc.z); acc.w = fmaf(v.w, m, acc.w);
-                }
-                if (active) {
-                    cc.x = fmaf(lam, acc.x, cc.x); cc.y = fmaf(lam, acc.y, cc.y);
-                    cc.z = fmaf(lam, acc.z, cc.z); cc.w = fmaf(lam, acc.w, cc.w);
-                    st4(cw + L::at(lr, q), cc);
-                    st4(bw + L::at(lr, q), own);
-                }
+        // ---------------- requests: H rows of this patch -> c_tile; the next patch's scalars -> scal, rows -> L2
+        rows_async(h, patch);
+        if (next < n_patches) {
+            scalars_async(next);
+            const size_t base = (size_t)next * TILE * KP;
+            const int lines = min(TILE, n_rows - next * TILE) * KP / 32;       // 128-byte lines of the patch's rows
+            for (int l = threadIdx.x; l < lines; l += TILE) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(beta_in + base + (size_t)l * 32));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(h + base + (size_t)l * 32));
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[pair][st][0]);
         }
-    } else {
-        // ================= consumer: one spot per lane, cyclic coordinate descent (direct form, FFMA2)
-        int n = 0;
-        for (int tile = pair_global; tile < n_tiles; tile += pair_stride, ++n) {
-            const int st = n & 1;
-            float *cw = pair_smem + st * L::kStageFloats;
-            float *bw = cw + 32 * L::S;
-            const int *dw = reinterpret_cast<const int *>(bw + 32 * L::S);
-            const int wbase = tile * 32;
-            mbar_wait(&bars[pair][st][0], (n >> 1) & 1);
-            const float lam_deg = lam * (float)dw[lane];
-            float2 b2[KP / 2];
+        asm volatile("cp.async.commit_group;");
+
+        // ---------------- neighbour sums from the fp16 gather tile, one spot per lane
+        __half2 acc[KP / 2];
+        {
 #pragma unroll
-            for (int qq = 0; qq < Q; ++qq) {
-                const float4 b4 = ld4(bw + L::at(lane, qq));
-                b2[2 * qq] = make_float2(b4.x, b4.y);
-                b2[2 * qq + 1] = make_float2(b4.z, b4.w);
+            for (int i = 0; i < KP / 2; ++i) acc[i] = __floats2half2_rn(0.f, 0.f);
+            const int rs = my_s - ibase;
+            const int maxdeg = __reduce_max_sync(kFull, my_deg);
+#pragma unroll 1
+            for (int u = 0; u < maxdeg; ++u) {
+                const bool has = u < my_deg;
+                unsigned code = own;
+                if (has) code = staged ? iw[rs + u] : plan.codes[my_s + u];
+                if (__any_sync(kFull, code == kCodeSlow)) {  // rare: more foreign rows than halo slots -> fp32 row from global
+                    if (code == kCodeSlow) {
+                        const float *src = beta_in + (size_t)__ldg(indices + my_s + u) * KP;
+#pragma unroll
+                        for (int q = 0; q < Q; ++q) {
+                            const float4 v = ld4(src + 4 * q);
+                            acc[2 * q] = __hadd2(acc[2 * q], __floats2half2_rn(v.x, v.y));
+                            acc[2 * q + 1] = __hadd2(acc[2 * q + 1], __floats2half2_rn(v.z, v.w));
+                        }
+                    }
+                }
+                // lanes without a (shared-memory) neighbour this round re-read their own row with weight 0
+                const bool use = has && code != kCodeSlow;
+                const __half2 m = use ? __floats2half2_rn(1.f, 1.f) : __floats2half2_rn(0.f, 0.f);
+                const int grow = use ? (int)code : own;
+                const uint4 *row = reinterpret_cast<const uint4 *>(g_tile + grow * GROW);
+                const int sw = gsw<GQ>(grow);
+#pragma unroll
+                for (int q = 0; q < GQ; ++q) {
+                    const uint4 w = row[q ^ sw];
+                    acc[4 * q] = __hfma2(*reinterpret_cast<const __half2 *>(&w.x), m, acc[4 * q]);
+                    acc[4 * q + 1] = __hfma2(*reinterpret_cast<const __half2 *>(&w.y), m, acc[4 * q + 1]);
+                    acc[4 * q + 2] = __hfma2(*reinterpret_cast<const __half2 *>(&w.z), m, acc[4 * q + 2]);
+                    acc[4 * q + 3] = __hfma2(*reinterpret_cast<const __half2 *>(&w.w), m, acc[4 * q + 3]);
+                }
             }
-            float tdmax = 0.f, tamax = 0.f;
-#pragma unroll
-            for (int qq = 0; qq < Q; ++qq) {
-                const float4 c4 = ld4(cw + L::at(lane, qq));
+        }
+        asm volatile("cp.async.wait_all;");              // H rows of this patch, scalars of the next
+        __syncwarp();
+        // the next patch's halo rows and code slice -> L2
+        if (next < n_patches) {
+            const int nx_halo = scal[2 * TILE + threadIdx.x];
+            if (nx_halo >= 0) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(beta_in + (size_t)nx_halo * KP));
+                if (KP > 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(beta_in + (size_t)nx_halo * KP + 32));
+            }
+            if ((lane & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(plan.codes + scal[threadIdx.x]));
+        }
+
+        // ---------------- cyclic coordinate descent, direct form on packed FFMA2 (see bcd_sweep_h_kernel)
+        {
+            const float lam_deg = lam * (float)my_deg;
+            const float neg_rho = -rho;
+            float dm = 0.f;
+            static_for<0, Q>([&](auto qc) {
+                constexpr int q = decltype(qc)::value;
+                const float4 c4 = ld4(c_tile + L::at(own, q));
+                const float2 s01 = __half22float2(acc[2 * q]), s23 = __half22float2(acc[2 * q + 1]);
+                const float4 ns4 = make_float4(s01.x, s01.y, s23.x, s23.y);
                 float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int k = 4 * qq + j;
-                    if (k >= KP - 3 && k >= n_types) continue;              // padding columns stay zero (uniform)
-                    float2 a0 = make_float2(elem(c4, j), 0.f), a1 = make_float2(0.f, 0.f);
-#pragma unroll
-                    for (int jj = 0; jj < KP / 2; ++jj) {
-                        const float2 g = make_float2(G.g[k * KP + 2 * jj], G.g[k * KP + 2 * jj + 1]);
-                        if (jj & 1) ffma2(a1, g, b2[jj]); else ffma2(a0, g, b2[jj]);
-                    }
-                    const float part = (a0.x + a0.y) + (a1.x + a1.y);
-                    const float old = (k & 1) ? b2[k / 2].y : b2[k / 2].x;
+                static_for<0, 4>([&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    constexpr int k = 4 * q + j;
+                    if (k >= KP - 7 && k >= n_types) return;            // padding columns stay zero (warp-uniform)
                     const float den = G.diag[k] + lam_deg;
-                    float nv = 0.f;
-                    if (den > 1e-10f) {
-                        const float sh = part > rho ? part - rho : (part < -rho ? part + rho : 0.f);
-                        nv = fmaxf(0.f, __fdividef(sh, den));
+                    const float rinv = den > 1e-10f ? rcp_fast(den) : 0.f;   // core/solver.py:87-90
+                    u64 a0 = pack2(fmaf(lam, elem(ns4, j), elem(c4, j)), neg_rho), a1 = 0ull;
+                    constexpr int start = (k + 1) >> 1;
+                    static_for<0, NP>([&](auto ic) {
+                        constexpr int i = decltype(ic)::value;
+                        constexpr int jj = (start + i) % NP;
+                        const u64 g = pack2(G.g[k * KP + 2 * jj], G.g[k * KP + 2 * jj + 1]);
+                        if constexpr (i & 1) ffma2q(a1, g, bq[jj]); else ffma2q(a0, g, bq[jj]);
+                    });
+                    float lo, hi, s0, s1;
+                    unpack2(add2q(a0, a1), s0, s1);
+                    const float nv = fmaxf(0.f, (s0 + s1) * rinv);
+                    unpack2(bq[k >> 1], lo, hi);
+                    if constexpr (k & 1) {
+                        dm = fmaxf(dm, fabsf(nv - hi));
+                        bq[k >> 1] = pack2(lo, nv);
+                    } else {
+                        dm = fmaxf(dm, fabsf(nv - lo));
+                        bq[k >> 1] = pack2(nv, hi);
                     }
-                    tdmax = fmaxf(tdmax, fabsf(nv - old));
-                    tamax = fmaxf(tamax, fabsf(old));
-                    if (k & 1) b2[k / 2].y = nv; else b2[k / 2].x = nv;
                     set_elem(n4, j, nv);
-                }
-                st4(bw + L::at(lane, qq), n4);
-            }
-            if (wbase + lane < n_rows) { dmax = fmaxf(dmax, tdmax); amax = fmaxf(amax, tamax); }
-            __syncwarp();
-            // stream the 32 new rows out (coalesced), then release the stage
-#pragma unroll
-            for (int i = 0; i < Q; ++i) {
-                const int idx = lane + 32 * i;
-                const int lr = idx / Q, qq = idx - lr * Q;
-                if (wbase + lr < n_rows) st4(beta_out + (size_t)(wbase + lr) * KP + 4 * qq, ld4(bw + L::at(lr, qq)));
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[pair][st][1]);
+                });
+                st4(c_tile + L::at(own, q), n4);
+            });
+            if (my_row < n_rows) dmax = fmaxf(dmax, dm);
         }
-        const unsigned wd = __reduce_max_sync(kFull, __float_as_uint(dmax));
-        const unsigned wa = __reduce_max_sync(kFull, __float_as_uint(amax));
-        if (lane == 0) { red[0][pair] = wd; red[1][pair] = wa; }
+        __syncwarp();
+
+        // ---------------- stream the warp's new rows out
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+            const int idx = lane + 32 * i;
+            const int lr = idx / Q, q = idx - lr * Q;
+            const int p = tile_base + wrow + lr;
+            if (p < n_rows) st4(beta_out + (size_t)p * KP + 4 * q, ld4(c_tile + L::at(wrow + lr, q)));
+        }
     }
+
+    const unsigned wd = __reduce_max_sync(kFull, __float_as_uint(dmax));
+    const unsigned wa = __reduce_max_sync(kFull, __float_as_uint(amax));
+    if (lane == 0) { red[0][warp] = wd; red[1][warp] = wa; }
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned bd = 0u, ba = 0u;
 #pragma unroll
-        for (int w = 0; w < kWsPairs; ++w) { bd = max(bd, red[0][w]); ba = max(ba, red[1][w]); }
+        for (int w = 0; w < NW; ++w) { bd = max(bd, red[0][w]); ba = max(ba, red[1][w]); }
         if (bd > *reinterpret_cast<volatile unsigned *>(&state->max_diff_bits)) atomicMax(&state->max_diff_bits, bd);
         if (ba > *reinterpret_cast<volatile unsigned *>(&state->max_abs_bits)) atomicMax(&state->max_abs_bits, ba);
         if (finalize) {
@@ -827,25 +920,6 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
     for (int k = 0; k < KP; ++k) G.diag[k] = k < n_types ? host_gram[k * n_types + k] : 0.f;
     for (int k = 0; k < n_types; ++k)
         for (int a = 0; a < n_types; ++a) G.g[k * KP + a] = (a == k) ? 0.f : -host_gram[k * n_types + a];
-    static const bool use_ws = getenv("FDB_SWEEP_WS") != nullptr;
-    if constexpr (KP == 32) if (use_ws) {          // comparison kernel, built for Kp = 32 only
-        using L = WsLayout<KP>;
-        static int ctas_per_sm = 0;
-        if (!ctas_per_sm) {
-            FDB_CUDA(cudaFuncSetAttribute(bcd_sweep_ws_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)L::kSmemBytes));
-            FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, bcd_sweep_ws_kernel<KP>, kWsThreads,
-                                                                   L::kSmemBytes));
-            if (ctas_per_sm < 1) ctas_per_sm = 1;
-        }
-        const int64_t tiles = ceil_div(n_rows, 32);
-        const int grid = (int)std::min<int64_t>(ceil_div(tiles, kWsPairs), (int64_t)kNumSM * ctas_per_sm);
-        bcd_sweep_ws_kernel<KP><<<grid, kWsThreads, L::kSmemBytes, st>>>(h, G, beta_in, beta_out, indptr, indices,
-                                                                         (int)n_rows, n_types, lam, rho, tol,
-                                                                         finalize, state);
-        FDB_LAUNCH_CHECK("bcd_sweep_ws_kernel");
-        return FDB_OK;
-    }
     // tile size / gather unroll: production default first, the others are tuning variants (FDB_SWEEP_VARIANT)
     static const int variant = getenv("FDB_SWEEP_VARIANT") ? atoi(getenv("FDB_SWEEP_VARIANT")) : 0;
     auto go = [&](auto kern, int nw) -> int {
@@ -864,36 +938,45 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
         for (int k = 0; k < n_types; ++k) mean_diag += host_gram[k * n_types + k];
         mean_diag /= (float)n_types;
         const bool weak_coupling = lam * 8.f <= 0.02f * mean_diag;
-        if (plan != nullptr && ((variant == 0 && weak_coupling) || variant == 4)) {   // halo-staged fp16 gather tile
-            // 128-spot patches (4 warps); residency by row width: 6 CTAs/SM at 34 KB (Kp <= 32), 4 at 45 KB (Kp = 40),
-            // 3 at 50-66 KB (Kp >= 48).  FDB_SWEEP_TILE256 selects 256-spot patches (3 % slower at C3, 6 % less traffic)
+        if (plan != nullptr && ((variant == 0 && weak_coupling) || variant == 4 || variant == 6)) {
+            // halo-staged fp16 gather tile, 128-spot patches (4 warps); residency by row width: 6 CTAs/SM at 36 KB
+            // (Kp <= 32), 4 at 47 KB (Kp = 40), 3 at 56-70 KB (Kp >= 48)
             constexpr int NWH = 4;
             constexpr int MINB = KP <= 32 ? 6 : 3;
-            auto run = [&](auto kern, int nw) -> int {
-                const int tile = nw * 32;
-                const size_t smem = (size_t)tile * TileLayout<KP>::S * 4 + (size_t)2 * tile * (KP / 2) * 4 +
-                                    (size_t)nw * kIdxCap * 2;
-                const int64_t n_ctas = ceil_div(n_rows, tile);
-                const char *pbase = (const char *)plan;
-                PlanView pv;
-                pv.halo_cnt = (const int32_t *)(pbase + plan_off_cnt());
-                pv.halo_rows = (const int32_t *)(pbase + plan_off_rows(n_ctas));
-                pv.codes = (const uint16_t *)(pbase + plan_off_codes(n_ctas, tile));
-                FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                static const int pf_env = getenv("FDB_SWEEP_PREFETCH") ? atoi(getenv("FDB_SWEEP_PREFETCH")) : -1;
-                int resident = 0;
-                FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, tile, smem));
-                const int pf_stride = pf_env >= 0 ? pf_env : kNumSM * std::max(resident, 1) / 2;   // half a wave ahead
-                kern<<<(int)n_ctas, tile, smem, st>>>(h, G, beta_in, beta_out, indptr, indices, pv, (int)n_rows,
-                                                      n_types, lam, rho, tol, finalize, state, pf_stride);
-                FDB_LAUNCH_CHECK("bcd_sweep_h_kernel");
+            constexpr int tile = NWH * 32;
+            const int64_t n_ctas = ceil_div(n_rows, tile);
+            const char *pbase = (const char *)plan;
+            PlanView pv;
+            pv.halo_cnt = (const int32_t *)(pbase + plan_off_cnt());
+            pv.halo_rows = (const int32_t *)(pbase + plan_off_rows(n_ctas));
+            pv.codes = (const uint16_t *)(pbase + plan_off_codes(n_ctas, tile));
+            const size_t smem_rows = (size_t)tile * TileLayout<KP>::S * 4 + (size_t)2 * tile * (KP / 2) * 4;
+            if (variant != 4) {                            // production: persistent, software-pipelined
+                auto kern = bcd_sweep_p_kernel<KP, NWH, MINB>;
+                const size_t smem = smem_rows + (size_t)NWH * kIdxCap * 2 + (size_t)3 * tile * 4;
+                static int resident = 0;
+                if (!resident) {
+                    FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, tile, smem));
+                    if (resident < 1) resident = 1;
+                }
+                const int grid = (int)std::min<int64_t>(n_ctas, (int64_t)kNumSM * resident);
+                kern<<<grid, tile, smem, st>>>(h, G, beta_in, beta_out, indptr, indices, pv, (int)n_rows, n_types,
+                                               lam, rho, tol, finalize, state, (int)n_ctas);
+                FDB_LAUNCH_CHECK("bcd_sweep_p_kernel");
                 return FDB_OK;
-            };
-            if constexpr (KP <= 32) {
-                static const bool big = getenv("FDB_SWEEP_TILE256") != nullptr;
-                if (big) return run(bcd_sweep_h_kernel<KP, 8, 3>, 8);                // tuning: 256-spot patches, 3 CTAs/SM
             }
-            return run(bcd_sweep_h_kernel<KP, NWH, MINB>, NWH);
+            auto kern = bcd_sweep_h_kernel<KP, NWH, MINB>;  // comparison: one patch per CTA
+            const size_t smem = smem_rows + (size_t)NWH * kIdxCap * 2;
+            FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            static const int pf_env = getenv("FDB_SWEEP_PREFETCH") ? atoi(getenv("FDB_SWEEP_PREFETCH")) : -1;
+            int resident = 0;
+            FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, tile, smem));
+            const int pf_stride = pf_env >= 0 ? pf_env : kNumSM * std::max(resident, 1) / 2;   // half a wave ahead
+            kern<<<(int)n_ctas, tile, smem, st>>>(h, G, beta_in, beta_out, indptr, indices, pv, (int)n_rows,
+                                                  n_types, lam, rho, tol, finalize, state, pf_stride);
+            FDB_LAUNCH_CHECK("bcd_sweep_h_kernel");
+            return FDB_OK;
         }
     }
     if constexpr (KP <= 32) {
@@ -914,9 +997,13 @@ static int dispatch_sweep(const float *h, const float *host_gram, int n_types, c
         return launch_sweep<KP_>(h, host_gram, n_types, beta_in, beta_out, indptr, indices, n_rows,    \
                                  lam, rho, tol, finalize, state, plan, st);
     switch (fdb_padded_types(n_types)) {
+#ifdef FDB_DEV_ONLY_KP                                     // development builds: one row width only
+        FDB_SWEEP_CASE(FDB_DEV_ONLY_KP)
+#else
         FDB_SWEEP_CASE(4) FDB_SWEEP_CASE(8) FDB_SWEEP_CASE(12) FDB_SWEEP_CASE(16)
         FDB_SWEEP_CASE(20) FDB_SWEEP_CASE(24) FDB_SWEEP_CASE(28) FDB_SWEEP_CASE(32)
         FDB_SWEEP_CASE(40) FDB_SWEEP_CASE(48) FDB_SWEEP_CASE(56) FDB_SWEEP_CASE(64)
+#endif
     default:
         set_error("n_types must be in [1, %d], got %d", FDB_MAX_TYPES, n_types);
         return FDB_ERR_UNSUPPORTED;
@@ -1059,8 +1146,7 @@ static int plan_tile_rows(int n_types)
 {
     const int kp = fdb_padded_types(n_types);
     if (kp % 8 != 0) return 0;                         // no half gather tile for this row width: no plan needed
-    static const bool big = getenv("FDB_SWEEP_TILE256") != nullptr;        // tuning switch
-    return (kp <= 32 && big) ? 256 : 128;              // must match the dispatcher in launch_sweep
+    return 128;                                        // must match the dispatcher in launch_sweep
 }
 
 extern "C" __attribute__((visibility("default"))) int64_t fdb_bcd_plan_bytes(int64_t n_rows, int64_t nnz, int32_t n_types)
@@ -1068,7 +1154,7 @@ extern "C" __attribute__((visibility("default"))) int64_t fdb_bcd_plan_bytes(int
     const int tile = plan_tile_rows(n_types);
     if (tile == 0 || n_rows <= 0) return 0;
     const int64_t n_ctas = ceil_div(n_rows, tile);
-    return round_up(plan_off_codes(n_ctas, tile) + 2 * (nnz > 0 ? nnz : 1), 256);
+    return round_up(plan_off_codes(n_ctas, tile) + 2 * (nnz > 0 ? nnz : 1) + 32, 256);   // +32: 16-byte code chunks
 }
 
 extern "C" __attribute__((visibility("default"))) int fdb_bcd_plan_build(const int32_t *indptr, const int32_t *indices, int64_t n_rows,
@@ -1086,10 +1172,7 @@ extern "C" __attribute__((visibility("default"))) int fdb_bcd_plan_build(const i
     int32_t *cnt = (int32_t *)(pbase + plan_off_cnt());
     int32_t *rows = (int32_t *)(pbase + plan_off_rows(n_ctas));
     uint16_t *codes = (uint16_t *)(pbase + plan_off_codes(n_ctas, tile));
-    if (tile == 256)
-        bcd_plan_kernel<256><<<(int)n_ctas, 256, 0, (cudaStream_t)stream>>>(indptr, indices, (int)n_rows, cnt, rows, codes);
-    else
-        bcd_plan_kernel<128><<<(int)n_ctas, 128, 0, (cudaStream_t)stream>>>(indptr, indices, (int)n_rows, cnt, rows, codes);
+    bcd_plan_kernel<128><<<(int)n_ctas, 128, 0, (cudaStream_t)stream>>>(indptr, indices, (int)n_rows, cnt, rows, codes);
     FDB_LAUNCH_CHECK("bcd_plan_kernel");
     return FDB_OK;
 }
