@@ -315,25 +315,40 @@ __device__ __forceinline__ int gsw(int row)
 // For every CTA patch of `TILE` spots: the out-of-patch neighbour rows it needs (deduplicated, at most HCAP
 // = TILE of them) and, per neighbour reference in CSR order, a 16-bit code = row of the CTA's gather tile
 // (patch row, or TILE + halo slot) or 0xFFFF when the patch needs more than HCAP foreign rows.
+// The same codes are also kept per warp (32 consecutive rows), transposed and padded to the warp's largest
+// degree, as bytes: codes8[warp][u][lane], u < max degree <= kCodeRounds, 512 bytes per warp -- round u of the
+// gather reads one byte per lane, conflict-free, with no row-pointer arithmetic.  Byte values are gather-tile rows
+// directly: 0..127 patch row, 128 + slot (slot < kHaloSlots = 126) halo row, 254 = the all-zero row (padding; it
+// is halo slot 126, which is never assigned), 255 = slow (foreign row without a slot).
 constexpr int kPlanHash = 1024;
 constexpr unsigned short kCodeSlow = 0xFFFF;
+constexpr int kHaloSlots = 126;                    // usable halo slots per 128-spot patch
+constexpr int kCodeRounds = 16;                    // largest per-warp max degree with a transposed code block
+constexpr int kCodeZero8 = 254, kCodeSlow8 = 255;
 
 struct PlanView {
     const int32_t *halo_cnt;      // [n_ctas]
     const int32_t *halo_rows;     // [n_ctas * HCAP]
-    const uint16_t *codes;        // [nnz]
+    const uint16_t *codes;        // [nnz], CSR order
+    const uint8_t *codes8;        // [n_ctas * 4 warps * kCodeRounds * 32], transposed per warp
 };
 
 __host__ __device__ inline int64_t plan_off_cnt() { return 64; }
 __host__ __device__ inline int64_t plan_off_rows(int64_t n_ctas) { return 64 + round_up(n_ctas * 4, 16); }
-__host__ __device__ inline int64_t plan_off_codes(int64_t n_ctas, int tile) { return plan_off_rows(n_ctas) + n_ctas * tile * 4; }
+__host__ __device__ inline int64_t plan_off_codes8(int64_t n_ctas, int tile) { return round_up(plan_off_rows(n_ctas) + n_ctas * tile * 4, 512); }
+__host__ __device__ inline int64_t plan_off_codes(int64_t n_ctas, int tile)
+{
+    return plan_off_codes8(n_ctas, tile) + n_ctas * (tile / 32) * (kCodeRounds * 32);
+}
 
 template <int TILE>
 __global__ void __launch_bounds__(TILE)
 bcd_plan_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, int n_rows,
-                int32_t *__restrict__ halo_cnt, int32_t *__restrict__ halo_rows, uint16_t *__restrict__ codes)
+                int32_t *__restrict__ halo_cnt, int32_t *__restrict__ halo_rows, uint16_t *__restrict__ codes,
+                uint8_t *__restrict__ codes8)
 {
     constexpr int HCAP = TILE;
+    static_assert(TILE == 128, "byte codes assume 128-spot patches");
     __shared__ int keys[kPlanHash];
     __shared__ int slots[kPlanHash];
     __shared__ int count;
@@ -363,10 +378,14 @@ bcd_plan_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ 
         if (keys[i] >= 0) {
             const int slot = atomicAdd(&count, 1);
             slots[i] = slot;
-            if (slot < HCAP) halo_rows[(int64_t)blockIdx.x * HCAP + slot] = keys[i];
+            if (slot < kHaloSlots) halo_rows[(int64_t)blockIdx.x * HCAP + slot] = keys[i];
         }
     }
     __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int maxdeg = __reduce_max_sync(kFull, e - s);
+    uint8_t *c8 = codes8 + ((int64_t)blockIdx.x * (TILE / 32) + (threadIdx.x >> 5)) * (kCodeRounds * 32) + lane;
+    const bool transposed = maxdeg <= kCodeRounds;
     for (int j = s; j < e; ++j) {
         const int g = indices[j];
         const int rel = g - tile_base;
@@ -375,13 +394,16 @@ bcd_plan_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ 
             code = (unsigned short)rel;
         } else {
             const int pos = probe(g, false);
-            code = (pos >= 0 && slots[pos] < HCAP) ? (unsigned short)(TILE + slots[pos]) : kCodeSlow;
+            code = (pos >= 0 && slots[pos] < kHaloSlots) ? (unsigned short)(TILE + slots[pos]) : kCodeSlow;
         }
         codes[j] = code;
+        if (transposed) c8[(j - s) * 32] = code == kCodeSlow ? (uint8_t)kCodeSlow8 : (uint8_t)code;
     }
-    if (threadIdx.x == 0) halo_cnt[blockIdx.x] = min(count, HCAP);
+    if (transposed)
+        for (int u = e - s; u < maxdeg; ++u) c8[u * 32] = (uint8_t)kCodeZero8;
+    if (threadIdx.x == 0) halo_cnt[blockIdx.x] = min(count, kHaloSlots);
     // unused slots carry -1 so that the sweep kernel can fetch the list without knowing its length first
-    if ((int)threadIdx.x >= count) halo_rows[(int64_t)blockIdx.x * HCAP + threadIdx.x] = -1;
+    if ((int)threadIdx.x >= min(count, kHaloSlots)) halo_rows[(int64_t)blockIdx.x * HCAP + threadIdx.x] = -1;
 }
 
 template <int KP, int NW, int MINB>
@@ -651,8 +673,8 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
     extern __shared__ __align__(16) float sweep_smem[];
     float *c_tile = sweep_smem;                                                   // TILE x S fp32: beta_old, H, beta_new
     uint32_t *g_tile = reinterpret_cast<uint32_t *>(c_tile + TILE * S);           // (TILE + HCAP) x GROW words
-    uint16_t *idx_tile = reinterpret_cast<uint16_t *>(g_tile + (TILE + HCAP) * GROW);   // NW x kIdxCap codes
-    int *scal = reinterpret_cast<int *>(idx_tile + NW * kIdxCap);                 // 3 x TILE: row start, end, halo id
+    uint8_t *idx_tile = reinterpret_cast<uint8_t *>(g_tile + (TILE + HCAP) * GROW);     // NW x kCodeRounds x 32 byte codes
+    int *scal = reinterpret_cast<int *>(idx_tile + NW * kCodeRounds * 32);        // 3 x TILE: row start, end, halo id
     __shared__ unsigned red[2][NW];
 
     if (*reinterpret_cast<volatile int *>(&state->converged)) return;      // uniform across the grid
@@ -660,7 +682,7 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wrow = warp * 32;
     const int own = wrow + lane;
-    uint16_t *iw = idx_tile + warp * kIdxCap;
+    uint8_t *iw = idx_tile + warp * (kCodeRounds * 32) + lane;
 
     // asynchronous copy of the warp's 32 rows of `src` (patch `pp`) into c_tile
     auto rows_async = [&](const float *__restrict__ src, int pp) {
@@ -703,13 +725,13 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
         const int my_s = scal[threadIdx.x], my_e = scal[TILE + threadIdx.x];
         const int halo_id = scal[2 * TILE + threadIdx.x];
         const int my_deg = my_e - my_s;
-        // the warp's slice of neighbour codes, staged from the 8-element-aligned position below its first entry
-        const int ibase = __shfl_sync(kFull, my_s, 0) & ~7;
-        const int icnt = __reduce_max_sync(kFull, my_e) - ibase;
-        const bool staged = icnt <= kIdxCap;
-        if (staged && 8 * lane < icnt) {
-            const uint32_t d = (uint32_t)__cvta_generic_to_shared(iw + 8 * lane);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(plan.codes + ibase + 8 * lane));
+        // the warp's transposed byte codes: 32 bytes per gather round
+        const int maxdeg = __reduce_max_sync(kFull, my_deg);
+        const bool staged = maxdeg <= kCodeRounds;
+        if (staged && lane < 2 * maxdeg) {
+            const uint32_t d = (uint32_t)__cvta_generic_to_shared(iw + 15 * lane);          // iw + lane + 15 lane = 16-byte chunk
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d),
+                         "l"(plan.codes8 + ((size_t)patch * NW + warp) * (kCodeRounds * 32) + 16 * lane));
         }
         // the warp's beta_old rows -> c_tile (its rows of c_tile were streamed out at the end of the previous patch)
         rows_async(beta_in, patch);
@@ -765,42 +787,51 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
         }
         asm volatile("cp.async.commit_group;");
 
-        // ---------------- neighbour sums from the fp16 gather tile, one spot per lane
+        // ---------------- neighbour sums from the fp16 gather tile, one spot per lane.  Round u adds, for every
+        // lane, the gather-tile row named by its u-th byte code (padding codes name the all-zero row 254).
         __half2 acc[KP / 2];
         {
 #pragma unroll
             for (int i = 0; i < KP / 2; ++i) acc[i] = __floats2half2_rn(0.f, 0.f);
-            const int rs = my_s - ibase;
-            const int maxdeg = __reduce_max_sync(kFull, my_deg);
-#pragma unroll 1
-            for (int u = 0; u < maxdeg; ++u) {
-                const bool has = u < my_deg;
-                unsigned code = own;
-                if (has) code = staged ? iw[rs + u] : plan.codes[my_s + u];
-                if (__any_sync(kFull, code == kCodeSlow)) {  // rare: more foreign rows than halo slots -> fp32 row from global
-                    if (code == kCodeSlow) {
-                        const float *src = beta_in + (size_t)__ldg(indices + my_s + u) * KP;
-#pragma unroll
-                        for (int q = 0; q < Q; ++q) {
-                            const float4 v = ld4(src + 4 * q);
-                            acc[2 * q] = __hadd2(acc[2 * q], __floats2half2_rn(v.x, v.y));
-                            acc[2 * q + 1] = __hadd2(acc[2 * q + 1], __floats2half2_rn(v.z, v.w));
-                        }
-                    }
-                }
-                // lanes without a (shared-memory) neighbour this round re-read their own row with weight 0
-                const bool use = has && code != kCodeSlow;
-                const __half2 m = use ? __floats2half2_rn(1.f, 1.f) : __floats2half2_rn(0.f, 0.f);
-                const int grow = use ? (int)code : own;
+            auto add_row = [&](int grow) {
                 const uint4 *row = reinterpret_cast<const uint4 *>(g_tile + grow * GROW);
                 const int sw = gsw<GQ>(grow);
 #pragma unroll
                 for (int q = 0; q < GQ; ++q) {
                     const uint4 w = row[q ^ sw];
-                    acc[4 * q] = __hfma2(*reinterpret_cast<const __half2 *>(&w.x), m, acc[4 * q]);
-                    acc[4 * q + 1] = __hfma2(*reinterpret_cast<const __half2 *>(&w.y), m, acc[4 * q + 1]);
-                    acc[4 * q + 2] = __hfma2(*reinterpret_cast<const __half2 *>(&w.z), m, acc[4 * q + 2]);
-                    acc[4 * q + 3] = __hfma2(*reinterpret_cast<const __half2 *>(&w.w), m, acc[4 * q + 3]);
+                    acc[4 * q] = __hadd2(*reinterpret_cast<const __half2 *>(&w.x), acc[4 * q]);
+                    acc[4 * q + 1] = __hadd2(*reinterpret_cast<const __half2 *>(&w.y), acc[4 * q + 1]);
+                    acc[4 * q + 2] = __hadd2(*reinterpret_cast<const __half2 *>(&w.z), acc[4 * q + 2]);
+                    acc[4 * q + 3] = __hadd2(*reinterpret_cast<const __half2 *>(&w.w), acc[4 * q + 3]);
+                }
+            };
+            auto add_slow = [&](int u) {                 // foreign row without a halo slot: fp32 row from global
+                const float *src = beta_in + (size_t)__ldg(indices + my_s + u) * KP;
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const float4 v = ld4(src + 4 * q);
+                    acc[2 * q] = __hadd2(acc[2 * q], __floats2half2_rn(v.x, v.y));
+                    acc[2 * q + 1] = __hadd2(acc[2 * q + 1], __floats2half2_rn(v.z, v.w));
+                }
+            };
+            if (staged) {
+                int code = maxdeg > 0 ? iw[0] : kCodeZero8;
+#pragma unroll 1
+                for (int u = 0; u < maxdeg; ++u) {
+                    const int cur = code;
+                    code = iw[min(u + 1, kCodeRounds - 1) * 32];            // next round's code (stale past the end)
+                    if (__any_sync(kFull, cur == kCodeSlow8)) {              // rare
+                        if (cur == kCodeSlow8) add_slow(u);
+                    }
+                    add_row(cur == kCodeSlow8 ? kCodeZero8 : cur);
+                }
+            } else {                                     // a row with more than kCodeRounds neighbours: CSR-order codes
+#pragma unroll 1
+                for (int u = 0; u < maxdeg; ++u) {
+                    unsigned code = kCodeZero8;
+                    if (u < my_deg) code = plan.codes[my_s + u];
+                    if (code == kCodeSlow) { add_slow(u); code = kCodeZero8; }
+                    add_row((int)code);
                 }
             }
         }
@@ -813,7 +844,8 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(beta_in + (size_t)nx_halo * KP));
                 if (KP > 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(beta_in + (size_t)nx_halo * KP + 32));
             }
-            if ((lane & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(plan.codes + scal[threadIdx.x]));
+            if (lane < 4)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(plan.codes8 + ((size_t)next * NW + warp) * (kCodeRounds * 32) + 128 * lane));
         }
 
         // ---------------- cyclic coordinate descent, direct form on packed FFMA2 (see bcd_sweep_h_kernel)
@@ -950,10 +982,11 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
             pv.halo_cnt = (const int32_t *)(pbase + plan_off_cnt());
             pv.halo_rows = (const int32_t *)(pbase + plan_off_rows(n_ctas));
             pv.codes = (const uint16_t *)(pbase + plan_off_codes(n_ctas, tile));
+            pv.codes8 = (const uint8_t *)(pbase + plan_off_codes8(n_ctas, tile));
             const size_t smem_rows = (size_t)tile * TileLayout<KP>::S * 4 + (size_t)2 * tile * (KP / 2) * 4;
             if (variant != 4) {                            // production: persistent, software-pipelined
                 auto kern = bcd_sweep_p_kernel<KP, NWH, MINB>;
-                const size_t smem = smem_rows + (size_t)NWH * kIdxCap * 2 + (size_t)3 * tile * 4;
+                const size_t smem = smem_rows + (size_t)NWH * kCodeRounds * 32 + (size_t)3 * tile * 4;
                 static int resident = 0;
                 if (!resident) {
                     FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1172,7 +1205,9 @@ extern "C" __attribute__((visibility("default"))) int fdb_bcd_plan_build(const i
     int32_t *cnt = (int32_t *)(pbase + plan_off_cnt());
     int32_t *rows = (int32_t *)(pbase + plan_off_rows(n_ctas));
     uint16_t *codes = (uint16_t *)(pbase + plan_off_codes(n_ctas, tile));
-    bcd_plan_kernel<128><<<(int)n_ctas, 128, 0, (cudaStream_t)stream>>>(indptr, indices, (int)n_rows, cnt, rows, codes);
+    uint8_t *codes8 = (uint8_t *)(pbase + plan_off_codes8(n_ctas, tile));
+    bcd_plan_kernel<128><<<(int)n_ctas, 128, 0, (cudaStream_t)stream>>>(indptr, indices, (int)n_rows, cnt, rows, codes,
+                                                                        codes8);
     FDB_LAUNCH_CHECK("bcd_plan_kernel");
     return FDB_OK;
 }
