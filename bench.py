@@ -297,7 +297,7 @@ def main():
                 "ms_per_step": 1e3 * e2e_s},
         "gpu_launches": int(launches),
         "stage_ms": stage_ms,
-        "roofline": {"bound": "hbm", "kernel": "bcd_sweep_kernel", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "bcd_sweep_p_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": profiled_traffic(args.config, "bcd_sweep"),
                      "peak_source": peak_src,
                      "bytes_per_launch": sweep_bytes, "ms_per_launch": sweep_ms,

@@ -39,6 +39,14 @@ struct alignas(16) GramArg {
     float diag[KP];                 // G[k][k]
 };
 
+// Gram operand of the pair-step descent (bcd_sweep_p_kernel): rows 2m and 2m+1 interleaved column by column
+template <int KP>
+struct alignas(16) GramPairArg {
+    float g2[KP * KP];              // g2[(m*KP + j)*2 + r] = -G[2m+r][j] for j outside {2m, 2m+1}, else 0; zero padded
+    float cross[KP];                // cross[k] = -G[k][k^1]
+    float diag[KP];                 // G[k][k]
+};
+
 __device__ __forceinline__ float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 __device__ __forceinline__ void add4(float4 &a, const float4 b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
@@ -638,6 +646,35 @@ bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
     }
 }
 
+__device__ __forceinline__ u64 packm(float lo, float hi)                // explicit mov.b64: the pair is assembled once
+{
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpackm(u64 v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 fma2(const u64 a, const u64 b, const u64 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 mul2q(const u64 a, const u64 b)
+{
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 sub2q(const u64 a, const u64 b)
+{
+    u64 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 // ------------------------------------------------------------------------------------
 // Sweep kernel, persistent software-pipelined form (production for Kp % 8 == 0).
 //
@@ -656,9 +693,16 @@ bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
 // Per patch: two CTA barriers (gather tile free / gather tile complete); statistics stay in registers until
 // the CTA has finished all its patches.
 // ------------------------------------------------------------------------------------
-template <int KP, int NW, int MINB>
+// Descent in PAIR STEPS: steps k = 2m and 2m+1 share one accumulator pair (part_2m, part_2m+1) that is fed, for every
+// column j outside the pair, by ONE FFMA2 whose beta_j operand is a broadcast scalar register and whose Gram operand
+// is the uniform pair (-G[2m][j], -G[2m+1][j]) (FFMA2 R, R.F32, UR.F32x2): Kp-2 FFMA2 per two steps with no
+// horizontal reduction and no 64-bit re-packing of beta (it lives in Kp scalar registers); the two cross terms
+// G[2m][2m+1] beta_old and G[2m+1][2m] beta_new are scalar FFMAs in the short serial tail.  Columns are walked from
+// the least to the most recently updated one, so only the last links of the two chains wait for the previous pair.
+// PADC = trailing all-padding columns (Kp - K >= PADC) left out at compile time.
+template <int KP, int NW, int MINB, int PADC>
 __global__ void __launch_bounds__(NW * 32, MINB)
-bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP> G,
+bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPairArg<KP> G,
                    const float *__restrict__ beta_in, float *__restrict__ beta_out,
                    const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, PlanView plan,
                    int n_rows, int n_types, float lam, float rho, float tol, int finalize, SolveState *state,
@@ -763,14 +807,13 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
             to_gather(TILE + wrow + lr, q, hrow[i]);
             to_gather(wrow + lr, q, ld4(c_tile + L::at(wrow + lr, q)));
         }
-        // own beta_old row -> registers (fp32)
-        u64 bq[NP];
+        // own beta_old row -> registers (fp32 scalars)
+        float b[KP];
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
             const float4 b4 = ld4(c_tile + L::at(own, q));
             amax = fmaxf(amax, fmaxf(fmaxf(fabsf(b4.x), fabsf(b4.y)), fmaxf(fabsf(b4.z), fabsf(b4.w))));
-            bq[2 * q] = pack2(b4.x, b4.y);
-            bq[2 * q + 1] = pack2(b4.z, b4.w);
+            b[4 * q] = b4.x; b[4 * q + 1] = b4.y; b[4 * q + 2] = b4.z; b[4 * q + 3] = b4.w;
         }
         __syncthreads();                 // (2) gather tile complete; the warp's fp32 rows are consumed
 
@@ -848,45 +891,51 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(plan.codes8 + ((size_t)next * NW + warp) * (kCodeRounds * 32) + 128 * lane));
         }
 
-        // ---------------- cyclic coordinate descent, direct form on packed FFMA2 (see bcd_sweep_h_kernel)
+        // ---------------- cyclic coordinate descent in pair steps (see the kernel header):
+        //   part_k = c_k - rho - sum_{j != k} G_kj b_j  (b_j already updated for j < k),  b_k <- max(0, part_k / den_k)
+        // Padding columns need no special case: their H, beta and Gram entries are 0, so they stay exactly 0.
         {
             const float lam_deg = lam * (float)my_deg;
             const float neg_rho = -rho;
             float dm = 0.f;
             static_for<0, Q>([&](auto qc) {
                 constexpr int q = decltype(qc)::value;
+                if constexpr (4 * q >= KP - PADC) return;
                 const float4 c4 = ld4(c_tile + L::at(own, q));
                 const float2 s01 = __half22float2(acc[2 * q]), s23 = __half22float2(acc[2 * q + 1]);
                 const float4 ns4 = make_float4(s01.x, s01.y, s23.x, s23.y);
-                float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                static_for<0, 4>([&](auto jc) {
-                    constexpr int j = decltype(jc)::value;
-                    constexpr int k = 4 * q + j;
-                    if (k >= KP - 7 && k >= n_types) return;            // padding columns stay zero (warp-uniform)
-                    const float den = G.diag[k] + lam_deg;
-                    const float rinv = den > 1e-10f ? rcp_fast(den) : 0.f;   // core/solver.py:87-90
-                    u64 a0 = pack2(fmaf(lam, elem(ns4, j), elem(c4, j)), neg_rho), a1 = 0ull;
-                    constexpr int start = (k + 1) >> 1;
-                    static_for<0, NP>([&](auto ic) {
+                static_for<0, 2>([&](auto mc) {
+                    constexpr int m = 2 * q + decltype(mc)::value;         // pair index
+                    constexpr int k0 = 2 * m;
+                    if constexpr (k0 >= KP - PADC) return;
+                    if (k0 >= KP - 8 && k0 >= n_types) return;              // a pair of padding columns (warp-uniform)
+                    const float den0 = G.diag[k0] + lam_deg, den1 = G.diag[k0 + 1] + lam_deg;
+                    const float ri0 = den0 > 1e-10f ? rcp_fast(den0) : 0.f;      // core/solver.py:87-90
+                    const float ri1 = den1 > 1e-10f ? rcp_fast(den1) : 0.f;
+                    u64 a0 = pack2(fmaf(lam, elem(ns4, k0 & 3), elem(c4, k0 & 3)),
+                                   fmaf(lam, elem(ns4, (k0 & 3) + 1), elem(c4, (k0 & 3) + 1)));
+                    u64 a1 = pack2(neg_rho, neg_rho);
+                    static_for<2, KP>([&](auto ic) {
                         constexpr int i = decltype(ic)::value;
-                        constexpr int jj = (start + i) % NP;
-                        const u64 g = pack2(G.g[k * KP + 2 * jj], G.g[k * KP + 2 * jj + 1]);
-                        if constexpr (i & 1) ffma2q(a1, g, bq[jj]); else ffma2q(a0, g, bq[jj]);
+                        constexpr int jj = (k0 + i) % KP;                   // k0+2, ..., Kp-1, 0, ..., k0-1
+                        if constexpr (jj < KP - PADC) {
+                            const u64 g = pack2(G.g2[(m * KP + jj) * 2], G.g2[(m * KP + jj) * 2 + 1]);
+                            if constexpr (i & 1) a1 = fma2(g, pack2(b[jj], b[jj]), a1);
+                            else a0 = fma2(g, pack2(b[jj], b[jj]), a0);
+                        }
                     });
-                    float lo, hi, s0, s1;
-                    unpack2(add2q(a0, a1), s0, s1);
-                    const float nv = fmaxf(0.f, (s0 + s1) * rinv);
-                    unpack2(bq[k >> 1], lo, hi);
-                    if constexpr (k & 1) {
-                        dm = fmaxf(dm, fabsf(nv - hi));
-                        bq[k >> 1] = pack2(lo, nv);
-                    } else {
-                        dm = fmaxf(dm, fabsf(nv - lo));
-                        bq[k >> 1] = pack2(nv, hi);
-                    }
-                    set_elem(n4, j, nv);
+                    float p0, p1;
+                    unpack2(add2q(a0, a1), p0, p1);
+                    p0 = fmaf(G.cross[k0], b[k0 + 1], p0);
+                    const float nv0 = fmaxf(0.f, p0 * ri0);
+                    dm = fmaxf(dm, fabsf(nv0 - b[k0]));
+                    b[k0] = nv0;
+                    p1 = fmaf(G.cross[k0 + 1], nv0, p1);
+                    const float nv1 = fmaxf(0.f, p1 * ri1);
+                    dm = fmaxf(dm, fabsf(nv1 - b[k0 + 1]));
+                    b[k0 + 1] = nv1;
                 });
-                st4(c_tile + L::at(own, q), n4);
+                st4(c_tile + L::at(own, q), make_float4(b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]));
             });
             if (my_row < n_rows) dmax = fmaxf(dmax, dm);
         }
@@ -910,6 +959,325 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
         unsigned bd = 0u, ba = 0u;
 #pragma unroll
         for (int w = 0; w < NW; ++w) { bd = max(bd, red[0][w]); ba = max(ba, red[1][w]); }
+        if (bd > *reinterpret_cast<volatile unsigned *>(&state->max_diff_bits)) atomicMax(&state->max_diff_bits, bd);
+        if (ba > *reinterpret_cast<volatile unsigned *>(&state->max_abs_bits)) atomicMax(&state->max_abs_bits, ba);
+        if (finalize) {
+            __threadfence();
+            if (atomicAdd(&state->arrived, 1u) == gridDim.x - 1) {
+                __threadfence();
+                finalize_state(state, tol);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Sweep kernel, persistent pipelined form with TWO spots per lane (production for Kp % 8 == 0).
+//
+// Same pipeline as bcd_sweep_p_kernel (scalars, codes and rows of patch p+1 requested while p is computed), but
+// a CTA is 2 warps = 64 lanes for a 128-spot patch and lane l of warp w owns spots a = 64 w + l and b = a + 32.
+// The coordinate descent keeps beta as pairs ACROSS the two spots, bp[j] = (beta_a[j], beta_b[j]), so that
+//   * one FFMA2 is one column j for both spots and its Gram operand is a single broadcast uniform register
+//     (FFMA2 R, R.F32x2, UR.F32): one LDCU.128 feeds four FFMA2 -- half the constant loads per spot;
+//   * the accumulator halves ARE the two spots' partial sums: no horizontal reduction, and the updated pair
+//     (new_a, new_b) replaces bp[k] as a whole: no re-packing moves;
+//   * the rest of the step (threshold, reciprocal scale, max-norm statistics) runs on packed f32x2 too.
+// 64-thread CTAs at 6 per SM leave 168 registers per thread, so nothing spills.
+// ------------------------------------------------------------------------------------
+// PADC: trailing all-padding columns (Kp - K >= PADC) left out of the descent at compile time
+template <int KP, int MINB, int PADC>
+__global__ void __launch_bounds__(64, MINB)
+bcd_sweep_d_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP> G,
+                   const float *__restrict__ beta_in, float *__restrict__ beta_out,
+                   const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, PlanView plan,
+                   int n_rows, int n_types, float lam, float rho, float tol, int finalize, SolveState *state,
+                   int n_patches)
+{
+    static_assert(KP % 8 == 0, "half gather rows need Kp % 8 == 0");
+    using L = TileLayout<KP>;
+    constexpr int Q = L::Q, S = L::S, TILE = 128, HCAP = TILE, NT = 64;
+    constexpr int GQ = Q / 2;                            // 16-byte chunks per fp16 gather row
+    constexpr int GROW = KP / 2;                         // 32-bit words per gather row
+    extern __shared__ __align__(16) float sweep_smem[];
+    float *c_tile = sweep_smem;                                                   // TILE x S fp32: beta_old, H, beta_new
+    uint32_t *g_tile = reinterpret_cast<uint32_t *>(c_tile + TILE * S);           // (TILE + HCAP) x GROW words
+    uint8_t *idx_tile = reinterpret_cast<uint8_t *>(g_tile + (TILE + HCAP) * GROW);     // 4 groups x kCodeRounds x 32 codes
+    int *scal = reinterpret_cast<int *>(idx_tile + 4 * kCodeRounds * 32);         // 3 x TILE: row start, end, halo id
+    __shared__ unsigned red[2][2];
+
+    if (*reinterpret_cast<volatile int *>(&state->converged)) return;      // uniform across the grid
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wrow = warp * 64;                          // the warp's 64 rows of the patch
+    const int own_a = wrow + lane, own_b = own_a + 32;
+    uint8_t *iw_a = idx_tile + (2 * warp) * (kCodeRounds * 32) + lane;
+    uint8_t *iw_b = iw_a + kCodeRounds * 32;
+
+    // asynchronous copy of the warp's 64 rows of `src` (patch `pp`) into c_tile
+    auto rows_async = [&](const float *__restrict__ src, int pp) {
+#pragma unroll
+        for (int i = 0; i < 2 * Q; ++i) {
+            const int idx = lane + 32 * i;
+            const int lr = idx / Q, q = idx - lr * Q;
+            const int p = pp * TILE + wrow + lr;
+            const uint32_t d = (uint32_t)__cvta_generic_to_shared(c_tile + L::at(wrow + lr, q));
+            const int nbytes = p < n_rows ? 16 : 0;                               // rows past the end: zero fill
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d),
+                         "l"(src + (size_t)min(p, n_rows - 1) * KP + 4 * q), "r"(nbytes));
+        }
+    };
+    // row pointers of the lane's two spots and halo ids of its two halo slots (32 w + lane, 64 + 32 w + lane) of
+    // patch `pp` -> this thread's private words of scal
+    auto scalars_async = [&](int pp) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int lrow = own_a + 32 * half;
+            const int r = pp * TILE + lrow;
+            const int nb = r < n_rows ? 4 : 0;
+            const int32_t *src = indptr + min(r, n_rows - 1);
+            const uint32_t d = (uint32_t)__cvta_generic_to_shared(scal + lrow);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(nb));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + 4 * TILE), "l"(src + 1), "r"(nb));
+            const int slot = 64 * half + 32 * warp + lane;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::
+                         "r"((uint32_t)__cvta_generic_to_shared(scal + 2 * TILE + slot)),
+                         "l"(plan.halo_rows + (size_t)pp * HCAP + slot));
+        }
+    };
+
+    // everything patch `pp` needs at its start (its scalars are in scal): the warp's 64 beta_old rows and its 64
+    // halo rows into registers (coalesced; halo ids travel by shuffle), its two code blocks into idx_tile
+    auto load_patch = [&](int pp, float4 (&hrow)[2 * Q]) {
+        const int d_a = scal[TILE + own_a] - scal[own_a], d_b = scal[TILE + own_b] - scal[own_b];
+        const int m_a = __reduce_max_sync(kFull, d_a), m_b = __reduce_max_sync(kFull, d_b);
+        if (max(m_a, m_b) <= kCodeRounds) {              // transposed byte codes of the two 32-row groups
+            const uint8_t *src = plan.codes8 + ((size_t)pp * 4 + 2 * warp) * (kCodeRounds * 32) + 16 * lane;
+            if (lane < 2 * m_a)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::
+                             "r"((uint32_t)__cvta_generic_to_shared(iw_a + 15 * lane)), "l"(src));
+            if (lane < 2 * m_b)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::
+                             "r"((uint32_t)__cvta_generic_to_shared(iw_b + 15 * lane)), "l"(src + kCodeRounds * 32));
+        }
+        asm volatile("cp.async.commit_group;");
+        rows_async(beta_in, pp);
+        asm volatile("cp.async.commit_group;");
+        const int hid0 = scal[2 * TILE + 32 * warp + lane], hid1 = scal[2 * TILE + 64 + 32 * warp + lane];
+#pragma unroll
+        for (int i = 0; i < 2 * Q; ++i) {
+            const int idx = lane + 32 * i;
+            const int lr = idx / Q, q = idx - lr * Q;
+            const int g = __shfl_sync(kFull, lr < 32 ? hid0 : hid1, lr & 31);
+            hrow[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g >= 0) hrow[i] = ld4(beta_in + (size_t)g * KP + 4 * q);
+        }
+    };
+
+    int patch = blockIdx.x;
+    scalars_async(patch);
+    asm volatile("cp.async.commit_group;");
+    asm volatile("cp.async.wait_all;");
+
+    float dmax = 0.f, amax = 0.f;
+#pragma unroll 1
+    for (; patch < n_patches; patch += gridDim.x) {
+        const int tile_base = patch * TILE;
+        const int next = patch + gridDim.x;
+        const int sa = scal[own_a], ea = scal[TILE + own_a], sb = scal[own_b], eb = scal[TILE + own_b];
+        const int deg_a = ea - sa, deg_b = eb - sb;
+        const int md_a = __reduce_max_sync(kFull, deg_a), md_b = __reduce_max_sync(kFull, deg_b);
+        const bool staged = max(md_a, md_b) <= kCodeRounds;
+        float4 hrow[2 * Q];
+        load_patch(patch, hrow);
+        asm volatile("cp.async.wait_all;");              // the warp's beta_old rows and code blocks
+        __syncthreads();                 // (1) both warps are past the gather of the previous patch: g_tile is free
+        auto to_gather = [&](int grow, int q, const float4 bb) {
+            const __half2 lo = __floats2half2_rn(bb.x, bb.y), hi = __floats2half2_rn(bb.z, bb.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t *>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t *>(&hi);
+            *reinterpret_cast<uint2 *>(g_tile + grow * GROW + 4 * ((q >> 1) ^ gsw<GQ>(grow)) + 2 * (q & 1)) = pk;
+        };
+#pragma unroll
+        for (int i = 0; i < 2 * Q; ++i) {
+            const int idx = lane + 32 * i;
+            const int lr = idx / Q, q = idx - lr * Q;
+            const int slot = lr < 32 ? 32 * warp + lr : 64 + 32 * warp + (lr - 32);
+            to_gather(TILE + slot, q, hrow[i]);
+            to_gather(wrow + lr, q, ld4(c_tile + L::at(wrow + lr, q)));
+        }
+        // own beta_old rows -> registers, paired across the two spots
+        u64 bp[KP];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const float4 a4 = ld4(c_tile + L::at(own_a, q)), b4 = ld4(c_tile + L::at(own_b, q));
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(a4.x), fabsf(a4.y)), fmaxf(fabsf(a4.z), fabsf(a4.w))));
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(b4.x), fabsf(b4.y)), fmaxf(fabsf(b4.z), fabsf(b4.w))));
+            // through an f32x2 add: ptxas re-materialises a bare mov.b64 {a, b} in front of every FFMA2 that reads
+            // it (two MOVs per use), while the result of an arithmetic instruction stays in its aligned pair
+            bp[4 * q] = add2q(packm(a4.x, b4.x), 0ull);
+            bp[4 * q + 1] = add2q(packm(a4.y, b4.y), 0ull);
+            bp[4 * q + 2] = add2q(packm(a4.z, b4.z), 0ull);
+            bp[4 * q + 3] = add2q(packm(a4.w, b4.w), 0ull);
+        }
+        __syncthreads();                 // (2) gather tile complete; the fp32 rows are consumed
+
+        // ---------------- requests: H rows of this patch -> c_tile; the next patch's scalars -> scal, rows -> L2
+        rows_async(h, patch);
+        if (next < n_patches) {
+            scalars_async(next);
+            const size_t base = (size_t)next * TILE * KP;
+            const int lines = min(TILE, n_rows - next * TILE) * KP / 32;       // 128-byte lines of the patch's rows
+            for (int l = tid; l < lines; l += NT) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(beta_in + base + (size_t)l * 32));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(h + base + (size_t)l * 32));
+            }
+        }
+        asm volatile("cp.async.commit_group;");
+
+        // ---------------- neighbour sums from the fp16 gather tile: round u adds, for both spots of the lane, the
+        // gather-tile row named by the u-th byte code (the all-zero row 254 past the end of a list)
+        __half2 acc_a[KP / 2], acc_b[KP / 2];
+        {
+#pragma unroll
+            for (int i = 0; i < KP / 2; ++i) { acc_a[i] = __floats2half2_rn(0.f, 0.f); acc_b[i] = acc_a[i]; }
+            auto add_row = [&](__half2 (&acc)[KP / 2], int grow) {
+                const uint4 *row = reinterpret_cast<const uint4 *>(g_tile + grow * GROW);
+                const int sw = gsw<GQ>(grow);
+#pragma unroll
+                for (int q = 0; q < GQ; ++q) {
+                    const uint4 w = row[q ^ sw];
+                    acc[4 * q] = __hadd2(*reinterpret_cast<const __half2 *>(&w.x), acc[4 * q]);
+                    acc[4 * q + 1] = __hadd2(*reinterpret_cast<const __half2 *>(&w.y), acc[4 * q + 1]);
+                    acc[4 * q + 2] = __hadd2(*reinterpret_cast<const __half2 *>(&w.z), acc[4 * q + 2]);
+                    acc[4 * q + 3] = __hadd2(*reinterpret_cast<const __half2 *>(&w.w), acc[4 * q + 3]);
+                }
+            };
+            auto add_slow = [&](__half2 (&acc)[KP / 2], int pos) {     // foreign row without a halo slot: fp32 row from global
+                const float *src = beta_in + (size_t)__ldg(indices + pos) * KP;
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const float4 v = ld4(src + 4 * q);
+                    acc[2 * q] = __hadd2(acc[2 * q], __floats2half2_rn(v.x, v.y));
+                    acc[2 * q + 1] = __hadd2(acc[2 * q + 1], __floats2half2_rn(v.z, v.w));
+                }
+            };
+            const int rounds = max(md_a, md_b);
+            if (staged) {
+                int na = md_a > 0 ? (int)iw_a[0] : kCodeZero8, nb = md_b > 0 ? (int)iw_b[0] : kCodeZero8;
+#pragma unroll 2
+                for (int u = 0; u < rounds; ++u) {
+                    int ca = na, cb = nb;                                   // codes are fetched one round ahead
+                    na = u + 1 < md_a ? (int)iw_a[(u + 1) * 32] : kCodeZero8;
+                    nb = u + 1 < md_b ? (int)iw_b[(u + 1) * 32] : kCodeZero8;
+                    if (__any_sync(kFull, ca == kCodeSlow8 || cb == kCodeSlow8)) {      // rare
+                        if (ca == kCodeSlow8) { add_slow(acc_a, sa + u); ca = kCodeZero8; }
+                        if (cb == kCodeSlow8) { add_slow(acc_b, sb + u); cb = kCodeZero8; }
+                    }
+                    add_row(acc_a, ca);
+                    add_row(acc_b, cb);
+                }
+            } else {                                     // a row with more than kCodeRounds neighbours: CSR-order codes
+#pragma unroll 1
+                for (int u = 0; u < rounds; ++u) {
+                    unsigned ca = kCodeZero8, cb = kCodeZero8;
+                    if (u < deg_a) ca = plan.codes[sa + u];
+                    if (u < deg_b) cb = plan.codes[sb + u];
+                    if (ca == kCodeSlow) { add_slow(acc_a, sa + u); ca = kCodeZero8; }
+                    if (cb == kCodeSlow) { add_slow(acc_b, sb + u); cb = kCodeZero8; }
+                    add_row(acc_a, (int)ca);
+                    add_row(acc_b, (int)cb);
+                }
+            }
+        }
+        asm volatile("cp.async.wait_all;");              // H rows of this patch, scalars of the next
+        __syncwarp();
+        if (next < n_patches) {                          // the next patch's halo rows and code blocks -> L2
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int nx_halo = scal[2 * TILE + 64 * half + 32 * warp + lane];
+                if (nx_halo >= 0) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(beta_in + (size_t)nx_halo * KP));
+                    if (KP > 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(beta_in + (size_t)nx_halo * KP + 32));
+                }
+            }
+            if (tid < 16)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(plan.codes8 + (size_t)next * 4 * (kCodeRounds * 32) + 128 * tid));
+        }
+
+        // ---------------- cyclic coordinate descent for both spots, direct form:
+        //   part_k = c_k - rho - sum_{j != k} G_kj b_j  (b_j already updated for j < k),  b_k <- max(0, part_k / den_k)
+        // Two accumulation chains per step walk the columns from the least to the most recently updated one
+        // (j = k+1, ..., Kp-1, 0, ..., k-1), so only the last link of each chain waits for step k-1.
+        {
+            const float ld_a = lam * (float)deg_a, ld_b = lam * (float)deg_b;
+            const u64 nrho2 = packm(-rho, -rho);
+            const u64 lam2 = packm(lam, lam);
+            u64 dm2 = 0ull;
+            static_for<0, Q>([&](auto qc) {
+                constexpr int q = decltype(qc)::value;
+                const float4 ca4 = ld4(c_tile + L::at(own_a, q)), cb4 = ld4(c_tile + L::at(own_b, q));
+                const float2 sa01 = __half22float2(acc_a[2 * q]), sa23 = __half22float2(acc_a[2 * q + 1]);
+                const float2 sb01 = __half22float2(acc_b[2 * q]), sb23 = __half22float2(acc_b[2 * q + 1]);
+                const float4 nsa = make_float4(sa01.x, sa01.y, sa23.x, sa23.y), nsb = make_float4(sb01.x, sb01.y, sb23.x, sb23.y);
+                float4 na4 = make_float4(0.f, 0.f, 0.f, 0.f), nb4 = na4;
+                static_for<0, 4>([&](auto jc) {
+                    constexpr int j = decltype(jc)::value;
+                    constexpr int k = 4 * q + j;
+                    if constexpr (k >= KP - PADC) return;               // padding columns stay zero
+                    if (k >= KP - 7 && k >= n_types) return;            // (warp-uniform)
+                    const float den_a = G.diag[k] + ld_a, den_b = G.diag[k] + ld_b;
+                    const float ri_a = den_a > 1e-10f ? rcp_fast(den_a) : 0.f;      // core/solver.py:87-90
+                    const float ri_b = den_b > 1e-10f ? rcp_fast(den_b) : 0.f;
+                    u64 a0 = fma2(packm(elem(nsa, j), elem(nsb, j)), lam2, packm(elem(ca4, j), elem(cb4, j)));
+                    u64 a1 = nrho2;
+                    static_for<1, KP>([&](auto ic) {
+                        constexpr int i = decltype(ic)::value;
+                        constexpr int jj = (k + i) % KP;
+                        if constexpr (jj < KP - PADC) {
+                            const float g = G.g[k * KP + jj];
+                            if constexpr (i & 1) a1 = fma2(pack2(g, g), bp[jj], a1); else a0 = fma2(pack2(g, g), bp[jj], a0);
+                        }
+                    });
+                    const u64 t2 = mul2q(add2q(a0, a1), packm(ri_a, ri_b));
+                    float ta, tb;
+                    unpackm(t2, ta, tb);
+                    const u64 nv2 = packm(fmaxf(0.f, ta), fmaxf(0.f, tb));
+                    const u64 d2 = sub2q(nv2, bp[k]);
+                    float da, db;
+                    unpackm(d2, da, db);
+                    float m0, m1;
+                    unpackm(dm2, m0, m1);
+                    dm2 = packm(fmaxf(m0, fabsf(da)), fmaxf(m1, fabsf(db)));
+                    bp[k] = nv2;
+                    set_elem(na4, j, fmaxf(0.f, ta));
+                    set_elem(nb4, j, fmaxf(0.f, tb));
+                });
+                st4(c_tile + L::at(own_a, q), na4);
+                st4(c_tile + L::at(own_b, q), nb4);
+            });
+            float m0, m1;
+            unpackm(dm2, m0, m1);
+            if (tile_base + own_a < n_rows) dmax = fmaxf(dmax, m0);
+            if (tile_base + own_b < n_rows) dmax = fmaxf(dmax, m1);
+        }
+        __syncwarp();
+
+#pragma unroll
+        for (int i = 0; i < 2 * Q; ++i) {
+            const int idx = lane + 32 * i;
+            const int lr = idx / Q, q = idx - lr * Q;
+            const int p = tile_base + wrow + lr;
+            if (p < n_rows) st4(beta_out + (size_t)p * KP + 4 * q, ld4(c_tile + L::at(wrow + lr, q)));
+        }
+    }
+
+    const unsigned wd = __reduce_max_sync(kFull, __float_as_uint(dmax));
+    const unsigned wa = __reduce_max_sync(kFull, __float_as_uint(amax));
+    if (lane == 0) { red[0][warp] = wd; red[1][warp] = wa; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned bd = max(red[0][0], red[0][1]), ba = max(red[1][0], red[1][1]);
         if (bd > *reinterpret_cast<volatile unsigned *>(&state->max_diff_bits)) atomicMax(&state->max_diff_bits, bd);
         if (ba > *reinterpret_cast<volatile unsigned *>(&state->max_abs_bits)) atomicMax(&state->max_abs_bits, ba);
         if (finalize) {
@@ -984,19 +1352,43 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
             pv.codes = (const uint16_t *)(pbase + plan_off_codes(n_ctas, tile));
             pv.codes8 = (const uint8_t *)(pbase + plan_off_codes8(n_ctas, tile));
             const size_t smem_rows = (size_t)tile * TileLayout<KP>::S * 4 + (size_t)2 * tile * (KP / 2) * 4;
-            if (variant != 4) {                            // production: persistent, software-pipelined
-                auto kern = bcd_sweep_p_kernel<KP, NWH, MINB>;
+            if (variant == 0 || KP != 32) {                // production: persistent, pipelined, pair-step descent
+                                                           // (the comparison kernels below are built for Kp = 32 only)
+                GramPairArg<KP> P;
+                for (int i = 0; i < KP * KP; ++i) P.g2[i] = 0.f;
+                for (int k = 0; k < KP; ++k) {
+                    P.diag[k] = G.diag[k];
+                    P.cross[k] = G.g[k * KP + (k ^ 1)];
+                    for (int j = 0; j < KP; ++j)
+                        if ((j >> 1) != (k >> 1)) P.g2[((k >> 1) * KP + j) * 2 + (k & 1)] = G.g[k * KP + j];
+                }
                 const size_t smem = smem_rows + (size_t)NWH * kCodeRounds * 32 + (size_t)3 * tile * 4;
-                static int resident = 0;
-                if (!resident) {
+                auto run_p = [&](auto kern) -> int {
+                    int resident = 0;
                     FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                     FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, tile, smem));
-                    if (resident < 1) resident = 1;
+                    const int grid = (int)std::min<int64_t>(n_ctas, (int64_t)kNumSM * std::max(resident, 1));
+                    kern<<<grid, tile, smem, st>>>(h, P, beta_in, beta_out, indptr, indices, pv, (int)n_rows, n_types,
+                                                   lam, rho, tol, finalize, state, (int)n_ctas);
+                    FDB_LAUNCH_CHECK("bcd_sweep_p_kernel");
+                    return FDB_OK;
+                };
+                if constexpr (KP <= 32 && KP >= 16) {      // K <= Kp - 2: the last two columns are padding
+                    if (n_types <= KP - 2) return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 2>);
                 }
-                const int grid = (int)std::min<int64_t>(n_ctas, (int64_t)kNumSM * resident);
-                kern<<<grid, tile, smem, st>>>(h, G, beta_in, beta_out, indptr, indices, pv, (int)n_rows, n_types,
-                                               lam, rho, tol, finalize, state, (int)n_ctas);
-                FDB_LAUNCH_CHECK("bcd_sweep_p_kernel");
+                return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 0>);
+            }
+            if constexpr (KP == 32) {
+            if (variant == 6) {                            // comparison: persistent, two spots per lane (12 warps/SM)
+                const size_t smem = smem_rows + (size_t)4 * kCodeRounds * 32 + (size_t)3 * tile * 4;
+                auto kern = bcd_sweep_d_kernel<KP, 6, 0>;
+                int resident = 0;
+                FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, 64, smem));
+                const int grid = (int)std::min<int64_t>(n_ctas, (int64_t)kNumSM * std::max(resident, 1));
+                kern<<<grid, 64, smem, st>>>(h, G, beta_in, beta_out, indptr, indices, pv, (int)n_rows, n_types,
+                                             lam, rho, tol, finalize, state, (int)n_ctas);
+                FDB_LAUNCH_CHECK("bcd_sweep_d_kernel");
                 return FDB_OK;
             }
             auto kern = bcd_sweep_h_kernel<KP, NWH, MINB>;  // comparison: one patch per CTA
@@ -1010,6 +1402,7 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
                                                   n_types, lam, rho, tol, finalize, state, pf_stride);
             FDB_LAUNCH_CHECK("bcd_sweep_h_kernel");
             return FDB_OK;
+            }
         }
     }
     if constexpr (KP <= 32) {
