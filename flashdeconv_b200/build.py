@@ -17,6 +17,8 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libfdb200.so")
 SOURCES = ["common.cu", "sketch.cu", "graph.cu", "bcd.cu", "comm.cu", "peer.cu"]
+# the production sweep kernel is fully unrolled per row width: one translation unit per Kp, widest (slowest) first
+SWEEP_KP = [64, 56, 48, 40, 32, 24, 16, 8]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -47,9 +49,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         common += ["-Xptxas", "-v"]
 
-    def one(src):
-        obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = common + ["-c", os.path.join(CSRC, src), "-o", obj]
+    def one(job):
+        src, defs, tag = job
+        obj = os.path.join(OBJ, src.replace(".cu", tag + ".o"))
+        cmd = common + defs + ["-c", os.path.join(CSRC, src), "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{res.stdout}\n{res.stderr}")
@@ -57,8 +60,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(res.stderr)
         return obj
 
-    with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        objs = list(ex.map(one, SOURCES))
+    jobs = [("bcd_p_inst.cu", [f"-DFDB_P_KP={kp}"], f"_{kp}") for kp in SWEEP_KP] + [(s, [], "") for s in SOURCES]
+    with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(one, jobs))
     link = [nvcc, "-shared", *ARCH, "-o", LIB + ".tmp", *objs, "-cudart", "static", "-ldl"]
     res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:

@@ -1,0 +1,347 @@
+// Production BCD sweep kernel (persistent, software-pipelined, pair-step descent) and its launcher.  One translation
+// unit per row width instantiates launch_sweep_p<KP> (bcd_p_inst.cu, compiled once per FDB_P_KP), so the eight
+// fully unrolled row widths build in parallel; bcd.cu only declares the launcher.
+#pragma once
+#include "bcd_common.cuh"
+
+namespace fdb {
+
+// ------------------------------------------------------------------------------------
+// Sweep kernel, persistent software-pipelined form (production for Kp % 8 == 0).
+//
+// bcd_sweep_h_kernel runs one patch per CTA, and because every CTA of a wave takes the same time the waves stay
+// in lock-step: all resident CTAs wait on their start-of-patch DRAM round trips together (37 % of the warp time
+// in the round-1 profile), then all compute together while HBM idles.  Here a CTA is persistent and walks
+// patches blockIdx.x, blockIdx.x + gridDim.x, ...; everything patch p+1 needs is requested while patch p is
+// being computed, with no extra shared memory for rows (residency stays at 6 CTAs/SM for Kp <= 32):
+//   * row pointers and halo row ids of p+1: plain loads into registers, consumed one iteration later;
+//   * neighbour codes of p+1: one 16-byte cp.async per lane into the alternate code buffer (after the gather of
+//     p, when the row pointers have landed);
+//   * beta_old rows, H rows and halo rows of p+1: prefetch.global.L2, so that the loads at the start of p+1 are
+//     L2 hits (the prefetched-ahead footprint of the whole grid is ~32 MB of the 126 MB L2);
+//   * H rows of p: cp.async into c_tile once the lane has its own beta_old row in registers, consumed after
+//     the gather; c_tile then receives beta_new and is streamed out.
+// Per patch: two CTA barriers (gather tile free / gather tile complete); statistics stay in registers until
+// the CTA has finished all its patches.
+// ------------------------------------------------------------------------------------
+// Descent in PAIR STEPS: steps k = 2m and 2m+1 share one accumulator pair (part_2m, part_2m+1) that is fed, for every
+// column j outside the pair, by ONE FFMA2 whose beta_j operand is a broadcast scalar register and whose Gram operand
+// is the uniform pair (-G[2m][j], -G[2m+1][j]) (FFMA2 R, R.F32, UR.F32x2): Kp-2 FFMA2 per two steps with no
+// horizontal reduction and no 64-bit re-packing of beta (it lives in Kp scalar registers); the two cross terms
+// G[2m][2m+1] beta_old and G[2m+1][2m] beta_new are scalar FFMAs in the short serial tail.  Columns are walked from
+// the least to the most recently updated one, so only the last links of the two chains wait for the previous pair.
+// PADC = trailing all-padding columns (Kp - K >= PADC) left out at compile time.
+template <int KP, int NW, int MINB, int PADC>
+__global__ void __launch_bounds__(NW * 32, MINB)
+bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPairArg<KP> G,
+                   const float *__restrict__ beta_in, float *__restrict__ beta_out,
+                   const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, PlanView plan,
+                   int n_rows, int n_types, float lam, float rho, float tol, int finalize, SolveState *state,
+                   int n_patches)
+{
+    static_assert(KP % 8 == 0, "half gather rows need Kp % 8 == 0");
+    using L = TileLayout<KP>;
+    constexpr int Q = L::Q, S = L::S, TILE = NW * 32, HCAP = TILE;
+    constexpr int GQ = Q / 2;                            // 16-byte chunks per fp16 gather row
+    constexpr int GROW = KP / 2;                         // 32-bit words per gather row
+    constexpr int NP = KP / 2;
+    extern __shared__ __align__(16) float sweep_smem[];
+    float *c_tile = sweep_smem;                                                   // TILE x S fp32: beta_old, H, beta_new
+    uint32_t *g_tile = reinterpret_cast<uint32_t *>(c_tile + TILE * S);           // (TILE + HCAP) x GROW words
+    uint8_t *idx_tile = reinterpret_cast<uint8_t *>(g_tile + (TILE + HCAP) * GROW);     // NW x kCodeRounds x 32 byte codes
+    int *scal = reinterpret_cast<int *>(idx_tile + NW * kCodeRounds * 32);        // 3 x TILE: row start, end, halo id
+    __shared__ unsigned red[2][NW];
+
+    if (*reinterpret_cast<volatile int *>(&state->converged)) return;      // uniform across the grid
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wrow = warp * 32;
+    const int own = wrow + lane;
+    uint8_t *iw = idx_tile + warp * (kCodeRounds * 32) + lane;
+
+    // asynchronous copy of the warp's 32 rows of `src` (patch `pp`) into c_tile
+    auto rows_async = [&](const float *__restrict__ src, int pp) {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+            const int idx = lane + 32 * i;
+            const int lr = idx / Q, q = idx - lr * Q;
+            const int p = pp * TILE + wrow + lr;
+            const uint32_t d = (uint32_t)__cvta_generic_to_shared(c_tile + L::at(wrow + lr, q));
+            const int nbytes = p < n_rows ? 16 : 0;                               // rows past the end: zero fill
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d),
+                         "l"(src + (size_t)min(p, n_rows - 1) * KP + 4 * q), "r"(nbytes));
+        }
+    };
+    // this thread's row pointers and halo row id of patch `pp` -> its three private words of `scal`
+    // (asynchronously: nothing is held in registers while the current patch is computed)
+    auto scalars_async = [&](int pp) {
+        const int r = pp * TILE + own;
+        const int nb = r < n_rows ? 4 : 0;
+        const int32_t *src = indptr + min(r, n_rows - 1);
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(scal + threadIdx.x);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(nb));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + 4 * TILE), "l"(src + 1), "r"(nb));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 8 * TILE),
+                     "l"(plan.halo_rows + (size_t)pp * HCAP + threadIdx.x));    // slot = thread, -1 = unused
+    };
+
+    // ---------------- prologue: the first patch's scalars
+    int patch = blockIdx.x;
+    scalars_async(patch);
+    asm volatile("cp.async.commit_group;");
+    asm volatile("cp.async.wait_all;");
+
+    float dmax = 0.f, amax = 0.f;
+#pragma unroll 1
+    for (; patch < n_patches; patch += gridDim.x) {
+        const int tile_base = patch * TILE;
+        const int next = patch + gridDim.x;
+        const int my_row = tile_base + own;
+        const int my_s = scal[threadIdx.x], my_e = scal[TILE + threadIdx.x];
+        const int halo_id = scal[2 * TILE + threadIdx.x];
+        const int my_deg = my_e - my_s;
+        // the warp's transposed byte codes: 32 bytes per gather round
+        const int maxdeg = __reduce_max_sync(kFull, my_deg);
+        const bool staged = maxdeg <= kCodeRounds;
+        if (staged && lane < 2 * maxdeg) {
+            const uint32_t d = (uint32_t)__cvta_generic_to_shared(iw + 15 * lane);          // iw + lane + 15 lane = 16-byte chunk
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d),
+                         "l"(plan.codes8 + ((size_t)patch * NW + warp) * (kCodeRounds * 32) + 16 * lane));
+        }
+        // the warp's beta_old rows -> c_tile (its rows of c_tile were streamed out at the end of the previous patch)
+        rows_async(beta_in, patch);
+        asm volatile("cp.async.commit_group;");
+        // the patch's halo rows (ids travel by shuffle); like everything above these are L2 hits: the lines were
+        // prefetched while the previous patch was computed
+        float4 hrow[Q];
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+            const int idx = lane + 32 * i;
+            const int lr = idx / Q, q = idx - lr * Q;
+            const int g = __shfl_sync(kFull, halo_id, lr);
+            hrow[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (g >= 0) hrow[i] = ld4(beta_in + (size_t)g * KP + 4 * q);
+        }
+        asm volatile("cp.async.wait_all;");
+        __syncthreads();                 // (1) every warp is past the gather of the previous patch: g_tile is free
+        auto to_gather = [&](int grow, int q, const float4 bb) {
+            const __half2 lo = __floats2half2_rn(bb.x, bb.y), hi = __floats2half2_rn(bb.z, bb.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t *>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t *>(&hi);
+            *reinterpret_cast<uint2 *>(g_tile + grow * GROW + 4 * ((q >> 1) ^ gsw<GQ>(grow)) + 2 * (q & 1)) = pk;
+        };
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+            const int idx = lane + 32 * i;
+            const int lr = idx / Q, q = idx - lr * Q;
+            to_gather(TILE + wrow + lr, q, hrow[i]);
+            to_gather(wrow + lr, q, ld4(c_tile + L::at(wrow + lr, q)));
+        }
+        // own beta_old row -> registers (fp32 scalars)
+        float b[KP];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const float4 b4 = ld4(c_tile + L::at(own, q));
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(b4.x), fabsf(b4.y)), fmaxf(fabsf(b4.z), fabsf(b4.w))));
+            b[4 * q] = b4.x; b[4 * q + 1] = b4.y; b[4 * q + 2] = b4.z; b[4 * q + 3] = b4.w;
+        }
+        __syncthreads();                 // (2) gather tile complete; the warp's fp32 rows are consumed
+
+        // ---------------- requests: H rows of this patch -> c_tile; the next patch's scalars -> scal, rows -> L2
+        rows_async(h, patch);
+        if (next < n_patches) {
+            scalars_async(next);
+            const size_t base = (size_t)next * TILE * KP;
+            const int lines = min(TILE, n_rows - next * TILE) * KP / 32;       // 128-byte lines of the patch's rows
+            for (int l = threadIdx.x; l < lines; l += TILE) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(beta_in + base + (size_t)l * 32));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(h + base + (size_t)l * 32));
+            }
+        }
+        asm volatile("cp.async.commit_group;");
+
+        // ---------------- neighbour sums from the fp16 gather tile, one spot per lane.  Round u adds, for every
+        // lane, the gather-tile row named by its u-th byte code (padding codes name the all-zero row 254).
+        __half2 acc[KP / 2];
+        {
+#pragma unroll
+            for (int i = 0; i < KP / 2; ++i) acc[i] = __floats2half2_rn(0.f, 0.f);
+            auto add_row = [&](int grow) {
+                const uint4 *row = reinterpret_cast<const uint4 *>(g_tile + grow * GROW);
+                const int sw = gsw<GQ>(grow);
+#pragma unroll
+                for (int q = 0; q < GQ; ++q) {
+                    const uint4 w = row[q ^ sw];
+                    acc[4 * q] = __hadd2(*reinterpret_cast<const __half2 *>(&w.x), acc[4 * q]);
+                    acc[4 * q + 1] = __hadd2(*reinterpret_cast<const __half2 *>(&w.y), acc[4 * q + 1]);
+                    acc[4 * q + 2] = __hadd2(*reinterpret_cast<const __half2 *>(&w.z), acc[4 * q + 2]);
+                    acc[4 * q + 3] = __hadd2(*reinterpret_cast<const __half2 *>(&w.w), acc[4 * q + 3]);
+                }
+            };
+            auto add_slow = [&](int u) {                 // foreign row without a halo slot: fp32 row from global
+                const float *src = beta_in + (size_t)__ldg(indices + my_s + u) * KP;
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    const float4 v = ld4(src + 4 * q);
+                    acc[2 * q] = __hadd2(acc[2 * q], __floats2half2_rn(v.x, v.y));
+                    acc[2 * q + 1] = __hadd2(acc[2 * q + 1], __floats2half2_rn(v.z, v.w));
+                }
+            };
+            if (staged) {
+                int code = maxdeg > 0 ? iw[0] : kCodeZero8;
+#pragma unroll 1
+                for (int u = 0; u < maxdeg; ++u) {
+                    const int cur = code;
+                    code = iw[min(u + 1, kCodeRounds - 1) * 32];            // next round's code (stale past the end)
+                    if (__any_sync(kFull, cur == kCodeSlow8)) {              // rare
+                        if (cur == kCodeSlow8) add_slow(u);
+                    }
+                    add_row(cur == kCodeSlow8 ? kCodeZero8 : cur);
+                }
+            } else {                                     // a row with more than kCodeRounds neighbours: CSR-order codes
+#pragma unroll 1
+                for (int u = 0; u < maxdeg; ++u) {
+                    unsigned code = kCodeZero8;
+                    if (u < my_deg) code = plan.codes[my_s + u];
+                    if (code == kCodeSlow) { add_slow(u); code = kCodeZero8; }
+                    add_row((int)code);
+                }
+            }
+        }
+        asm volatile("cp.async.wait_all;");              // H rows of this patch, scalars of the next
+        __syncwarp();
+        // the next patch's halo rows and code slice -> L2
+        if (next < n_patches) {
+            const int nx_halo = scal[2 * TILE + threadIdx.x];
+            if (nx_halo >= 0) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(beta_in + (size_t)nx_halo * KP));
+                if (KP > 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(beta_in + (size_t)nx_halo * KP + 32));
+            }
+            if (lane < 4)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(plan.codes8 + ((size_t)next * NW + warp) * (kCodeRounds * 32) + 128 * lane));
+        }
+
+        // ---------------- cyclic coordinate descent in pair steps (see the kernel header):
+        //   part_k = c_k - rho - sum_{j != k} G_kj b_j  (b_j already updated for j < k),  b_k <- max(0, part_k / den_k)
+        // Padding columns need no special case: their H, beta and Gram entries are 0, so they stay exactly 0.
+        {
+            const float lam_deg = lam * (float)my_deg;
+            const float neg_rho = -rho;
+            float dm = 0.f;
+            static_for<0, Q>([&](auto qc) {
+                constexpr int q = decltype(qc)::value;
+                if constexpr (4 * q >= KP - PADC) return;
+                const float4 c4 = ld4(c_tile + L::at(own, q));
+                const float2 s01 = __half22float2(acc[2 * q]), s23 = __half22float2(acc[2 * q + 1]);
+                const float4 ns4 = make_float4(s01.x, s01.y, s23.x, s23.y);
+                static_for<0, 2>([&](auto mc) {
+                    constexpr int m = 2 * q + decltype(mc)::value;         // pair index
+                    constexpr int k0 = 2 * m;
+                    if constexpr (k0 >= KP - PADC) return;
+                    if (k0 >= KP - 8 && k0 >= n_types) return;              // a pair of padding columns (warp-uniform)
+                    const float den0 = G.diag[k0] + lam_deg, den1 = G.diag[k0 + 1] + lam_deg;
+                    const float ri0 = den0 > 1e-10f ? rcp_fast(den0) : 0.f;      // core/solver.py:87-90
+                    const float ri1 = den1 > 1e-10f ? rcp_fast(den1) : 0.f;
+                    u64 a0 = pack2(fmaf(lam, elem(ns4, k0 & 3), elem(c4, k0 & 3)),
+                                   fmaf(lam, elem(ns4, (k0 & 3) + 1), elem(c4, (k0 & 3) + 1)));
+                    u64 a1 = pack2(neg_rho, neg_rho);
+                    static_for<2, KP>([&](auto ic) {
+                        constexpr int i = decltype(ic)::value;
+                        constexpr int jj = (k0 + i) % KP;                   // k0+2, ..., Kp-1, 0, ..., k0-1
+                        if constexpr (jj < KP - PADC) {
+                            const u64 g = pack2(G.g2[(m * KP + jj) * 2], G.g2[(m * KP + jj) * 2 + 1]);
+                            if constexpr (i & 1) a1 = fma2(g, pack2(b[jj], b[jj]), a1);
+                            else a0 = fma2(g, pack2(b[jj], b[jj]), a0);
+                        }
+                    });
+                    float p0, p1;
+                    unpack2(add2q(a0, a1), p0, p1);
+                    p0 = fmaf(G.cross[k0], b[k0 + 1], p0);
+                    const float nv0 = fmaxf(0.f, p0 * ri0);
+                    dm = fmaxf(dm, fabsf(nv0 - b[k0]));
+                    b[k0] = nv0;
+                    p1 = fmaf(G.cross[k0 + 1], nv0, p1);
+                    const float nv1 = fmaxf(0.f, p1 * ri1);
+                    dm = fmaxf(dm, fabsf(nv1 - b[k0 + 1]));
+                    b[k0 + 1] = nv1;
+                });
+                st4(c_tile + L::at(own, q), make_float4(b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]));
+            });
+            if (my_row < n_rows) dmax = fmaxf(dmax, dm);
+        }
+        __syncwarp();
+
+        // ---------------- stream the warp's new rows out
+#pragma unroll
+        for (int i = 0; i < Q; ++i) {
+            const int idx = lane + 32 * i;
+            const int lr = idx / Q, q = idx - lr * Q;
+            const int p = tile_base + wrow + lr;
+            if (p < n_rows) st4(beta_out + (size_t)p * KP + 4 * q, ld4(c_tile + L::at(wrow + lr, q)));
+        }
+    }
+
+    const unsigned wd = __reduce_max_sync(kFull, __float_as_uint(dmax));
+    const unsigned wa = __reduce_max_sync(kFull, __float_as_uint(amax));
+    if (lane == 0) { red[0][warp] = wd; red[1][warp] = wa; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned bd = 0u, ba = 0u;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { bd = max(bd, red[0][w]); ba = max(ba, red[1][w]); }
+        if (bd > *reinterpret_cast<volatile unsigned *>(&state->max_diff_bits)) atomicMax(&state->max_diff_bits, bd);
+        if (ba > *reinterpret_cast<volatile unsigned *>(&state->max_abs_bits)) atomicMax(&state->max_abs_bits, ba);
+        if (finalize) {
+            __threadfence();
+            if (atomicAdd(&state->arrived, 1u) == gridDim.x - 1) {
+                __threadfence();
+                finalize_state(state, tol);
+            }
+        }
+    }
+}
+
+
+// host side: Gram operand in pair-row layout, plan view, residency-sized persistent grid
+template <int KP>
+int launch_sweep_p(const float *h, const GramArg<KP> &G, int n_types, const float *beta_in, float *beta_out,
+                   const int32_t *indptr, const int32_t *indices, int64_t n_rows, float lam, float rho, float tol,
+                   int finalize, SolveState *state, const void *plan, cudaStream_t st)
+{
+    // 128-spot patches (4 warps); residency by row width (shared memory): 6 CTAs/SM at 36 KB (Kp <= 32), 4 at 46-54 KB
+    // (Kp = 40, 48), 3 at 62-68 KB (Kp = 56, 64)
+    constexpr int NWH = 4;
+    constexpr int MINB = KP <= 32 ? 6 : (KP <= 48 ? 4 : 3);
+    constexpr int tile = NWH * 32;
+    const int64_t n_ctas = ceil_div(n_rows, tile);
+    const PlanView pv = plan_view(plan, n_ctas, tile);
+    GramPairArg<KP> P;
+    for (int i = 0; i < KP * KP; ++i) P.g2[i] = 0.f;
+    for (int k = 0; k < KP; ++k) {
+        P.diag[k] = G.diag[k];
+        P.cross[k] = G.g[k * KP + (k ^ 1)];
+        for (int j = 0; j < KP; ++j)
+            if ((j >> 1) != (k >> 1)) P.g2[((k >> 1) * KP + j) * 2 + (k & 1)] = G.g[k * KP + j];
+    }
+    const size_t smem = (size_t)tile * TileLayout<KP>::S * 4 + (size_t)2 * tile * (KP / 2) * 4 +
+                        (size_t)NWH * kCodeRounds * 32 + (size_t)3 * tile * 4;
+    auto run_p = [&](auto kern) -> int {
+        int resident = 0;
+        FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, tile, smem));
+        const int grid = (int)std::min<int64_t>(n_ctas, (int64_t)kNumSM * std::max(resident, 1));
+        kern<<<grid, tile, smem, st>>>(h, P, beta_in, beta_out, indptr, indices, pv, (int)n_rows, n_types, lam, rho, tol,
+                                       finalize, state, (int)n_ctas);
+        FDB_LAUNCH_CHECK("bcd_sweep_p_kernel");
+        return FDB_OK;
+    };
+    // trailing padding columns (Kp - K, rounded down to even) are left out at compile time
+    const int pad = KP - n_types;
+    if (pad >= 6) return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 6>);
+    if (pad >= 4) return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 4>);
+    if (pad >= 2) return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 2>);
+    return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 0>);
+}
+
+}  // namespace fdb

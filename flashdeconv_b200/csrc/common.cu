@@ -25,10 +25,10 @@ int cuda_fail(cudaError_t e, const char *what)
 FDB_API int fdb_abi_version(void) { return 1; }
 FDB_API const char *fdb_last_error(void) { return fdb::g_err; }
 FDB_API long long fdb_launch_count(void) { return fdb::g_launches; }
-// rows are 16-byte aligned (multiple of 4 floats); above 32 types they are padded to a multiple of 8 so that the
-// half-precision gather rows of the sweep kernel are 16-byte aligned too
+// rows are padded to a multiple of 8 floats: 32-byte aligned fp32 rows and 16-byte aligned half-precision gather
+// rows, so that every K runs the halo-staged sweep kernel (padding columns are exactly 0 everywhere)
 FDB_API int fdb_padded_types(int n_types)
 {
     if (n_types <= 0) return 0;
-    return (int)fdb::round_up(n_types, n_types > 32 ? 8 : 4);
+    return (int)fdb::round_up(n_types, 8);
 }

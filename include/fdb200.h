@@ -21,8 +21,8 @@
  *   spots live in "tile order" (a spatially coherent permutation produced by
  *   fdb_graph_build); `order[p]` = original index of the spot at position p, `rank[i]` =
  *   position of original spot i.  Spot-by-type matrices (H, beta) are row-major
- *   n_rows x Kp float32 with Kp = fdb_padded_types(K) (K rounded up to a multiple of 4 -- of 8 above
- *   32 types -- so every row is 16-byte aligned); padding columns are zero.
+ *   n_rows x Kp float32 with Kp = fdb_padded_types(K) (K rounded up to a multiple of 8, so fp32
+ *   rows are 32-byte and their fp16 images 16-byte aligned); padding columns are zero.
  */
 #ifndef FDB200_H
 #define FDB200_H

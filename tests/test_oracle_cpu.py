@@ -171,7 +171,7 @@ def test_cabi_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(so, name), name
     assert _native.lib.fdb_abi_version() == 1
-    assert [_native.padded_types(k) for k in (1, 4, 5, 30, 33, 50, 64)] == [4, 4, 8, 32, 40, 56, 64]
+    assert [_native.padded_types(k) for k in (1, 4, 5, 30, 33, 50, 64)] == [8, 8, 8, 32, 40, 56, 64]
 
 
 def test_product_does_not_import_oracle():
