@@ -983,11 +983,40 @@ objective_kernel(const float *__restrict__ beta, const float *__restrict__ h, co
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     double cross = 0.0, quad = 0.0, lap = 0.0, l1 = 0.0, yy = 0.0;
     const bool on0 = lane < kp, on1 = NK == 2 && lane + 32 < kp;
+    // the chain row pointers -> neighbour ids -> neighbour rows is three dependent global round trips per spot; the
+    // pointers and the first 8 neighbour ids of the NEXT spot of this warp are fetched one iteration ahead
+    int s = 0, e = 0, nb0 = -1;                            // lane u < 8 holds neighbour u of the current spot
+    if (warp_global < n_rows) {
+        s = __ldg(indptr + warp_global); e = __ldg(indptr + warp_global + 1);
+        if (lane < 8 && s + lane < e) nb0 = __ldg(indices + s + lane);
+    }
     for (int64_t p = warp_global; p < n_rows; p += n_warps) {
+        const int64_t pn = p + n_warps;
+        int s2 = 0, e2 = 0;
+        if (pn < n_rows) { s2 = __ldg(indptr + pn); e2 = __ldg(indptr + pn + 1); }
         const float b0 = on0 ? beta[p * kp + lane] : 0.f;
         const float b1 = on1 ? beta[p * kp + 32 + lane] : 0.f;
         const float h0 = on0 ? h[p * kp + lane] : 0.f;
         const float h1 = on1 ? h[p * kp + 32 + lane] : 0.f;
+        float n0 = 0.f, n1 = 0.f;
+        for (int j0 = s; j0 < e; j0 += 8) {                 // 8 independent row reads in flight
+            int nb[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int pre = __shfl_sync(kFull, nb0, u);
+                nb[u] = j0 == s ? pre : (j0 + u < e ? __ldg(indices + j0 + u) : -1);
+            }
+            float v0[8], v1[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                v0[u] = (on0 && nb[u] >= 0) ? beta[(int64_t)nb[u] * kp + lane] : 0.f;
+                v1[u] = (on1 && nb[u] >= 0) ? beta[(int64_t)nb[u] * kp + 32 + lane] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { n0 += v0[u]; n1 += v1[u]; }
+        }
+        int nb2 = -1;
+        if (lane < 8 && s2 + lane < e2) nb2 = __ldg(indices + s2 + lane);     // lands while the Gram product runs
         float gb0 = 0.f, gb1 = 0.f;
         unsigned m = __ballot_sync(kFull, b0 != 0.f);
         while (m) {
@@ -1007,27 +1036,13 @@ objective_kernel(const float *__restrict__ beta, const float *__restrict__ h, co
                 if (on1) gb1 = fmaf(gs[(c + 32) * kp + 32 + lane], bc, gb1);
             }
         }
-        const int s = indptr[p], e = indptr[p + 1];
-        float n0 = 0.f, n1 = 0.f;
-        for (int j0 = s; j0 < e; j0 += 8) {                 // 8 independent row reads in flight
-            int nb[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) nb[u] = j0 + u < e ? __ldg(indices + j0 + u) : -1;
-            float v0[8], v1[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                v0[u] = (on0 && nb[u] >= 0) ? beta[(int64_t)nb[u] * kp + lane] : 0.f;
-                v1[u] = (on1 && nb[u] >= 0) ? beta[(int64_t)nb[u] * kp + 32 + lane] : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) { n0 += v0[u]; n1 += v1[u]; }
-        }
         const float deg = (float)(e - s);
         cross += (double)(b0 * h0) + (double)(b1 * h1);
         quad += (double)(b0 * gb0) + (double)(b1 * gb1);
         lap += (double)b0 * (double)(deg * b0 - n0) + (double)b1 * (double)(deg * b1 - n1);
         l1 += (double)fabsf(b0) + (double)fabsf(b1);
         if (lane == 0) yy += (double)ysq[p];
+        s = s2; e = e2; nb0 = nb2;
     }
     __shared__ double red[5][8];
     cross = warp_sum(cross); quad = warp_sum(quad); lap = warp_sum(lap); l1 = warp_sum(l1); yy = warp_sum(yy);

@@ -446,10 +446,7 @@ sketch_contract_v3_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
             const int t = t0 + lane;
             if (t < n) {
                 const int2 bw = slot_bw[list_s[t]];
-                // log1p: counts-per-10k values are >= 1 in practice, where MUFU-based __logf(1 + x) is good to 3 ulp;
-                // the exact log1pf path only runs for warps that meet a smaller argument
-                const float xv = list_v[t] * scale;
-                const float c = (xv >= 1.f ? __logf(1.f + xv) : log1pf(xv)) * __int_as_float(bw.y);
+                const float c = log1pf(list_v[t] * scale) * __int_as_float(bw.y);
                 atomicAdd(acc + bw.x, c);
                 const float4 *xr = reinterpret_cast<const float4 *>(xs + bw.x * XR);
 #pragma unroll
