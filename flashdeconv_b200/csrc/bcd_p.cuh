@@ -330,7 +330,9 @@ int launch_sweep_p(const float *h, const GramArg<KP> &G, int n_types, const floa
         int resident = 0;
         FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, tile, smem));
-        const int grid = (int)std::min<int64_t>(n_ctas, (int64_t)kNumSM * std::max(resident, 1));
+        // FDB_SWEEP_MAX_CTAS caps the persistent grid (tests: several patches per CTA on small problems)
+        static const int cap = getenv("FDB_SWEEP_MAX_CTAS") ? std::max(atoi(getenv("FDB_SWEEP_MAX_CTAS")), 1) : 1 << 30;
+        const int grid = (int)std::min<int64_t>(std::min<int64_t>(n_ctas, cap), (int64_t)kNumSM * std::max(resident, 1));
         kern<<<grid, tile, smem, st>>>(h, P, beta_in, beta_out, indptr, indices, pv, (int)n_rows, n_types, lam, rho, tol,
                                        finalize, state, (int)n_ctas);
         FDB_LAUNCH_CHECK("bcd_sweep_p_kernel");
