@@ -20,6 +20,11 @@
 
 namespace fdb {
 
+// value transform of the fused kernels: scale > 0 -> log1p(v * scale) (log-CPM, core/deconv.py:177-197); scale <= 0 ->
+// v itself (preprocess "raw" / "pearson": a per-gene factor folded into the gene weights, core/deconv.py:199-229)
+__device__ __forceinline__ float xform_value(float v, float scale) { return scale > 0.f ? log1pf(v * scale) : v; }
+
+
 constexpr int kCache = 16;   // register-cached chunks of 32 entries per row
 
 struct RowCache {
@@ -118,7 +123,7 @@ sketch_contract_kernel(const IndPtr *__restrict__ indptr, const int32_t *__restr
                        const float *__restrict__ gene_weight, int d,
                        const float *__restrict__ x_sketch_t, int kp,
                        const int32_t *__restrict__ row_map, const int32_t *__restrict__ row_ids,
-                       float *__restrict__ h, float *__restrict__ ysq)
+                       float *__restrict__ h, float *__restrict__ ysq, int linear)
 {
     extern __shared__ __align__(16) float smem[];
     const int lane = threadIdx.x & 31;
@@ -139,7 +144,8 @@ sketch_contract_kernel(const IndPtr *__restrict__ indptr, const int32_t *__restr
          it += (int64_t)gridDim.x * warps_per_cta) {
         const int64_t row = row_ids ? (int64_t)__ldg(row_ids + it) : it;       // input row processed by this warp
         const int64_t s = load_ptr(indptr, row), e = load_ptr(indptr, row + 1);
-        const float scale = 1e4f / row_pass1(indices, counts, gene_bucket, gene_weight, s, e, lane, rc);
+        const float lib1 = row_pass1(indices, counts, gene_bucket, gene_weight, s, e, lane, rc);
+        const float scale = linear ? -1.f : 1e4f / lib1;
         float h0 = 0.f, h1 = 0.f;
         auto consume = [&](int b, float c) {
             // every lane calls this with its own (b, c); selected entries are broadcast one by one
@@ -157,7 +163,7 @@ sketch_contract_kernel(const IndPtr *__restrict__ indptr, const int32_t *__restr
 #pragma unroll
         for (int c = 0; c < kCache; ++c) {
             if (s + 32 * c >= e) break;             // warp-uniform
-            consume(rc.b[c], rc.b[c] >= 0 ? log1pf(rc.v[c] * scale) * rc.w[c] : 0.f);
+            consume(rc.b[c], rc.b[c] >= 0 ? xform_value(rc.v[c], scale) * rc.w[c] : 0.f);
         }
         for (int64_t j0 = s + 32 * kCache; j0 < e; j0 += 32) {
             const int64_t j = j0 + lane;
@@ -166,7 +172,7 @@ sketch_contract_kernel(const IndPtr *__restrict__ indptr, const int32_t *__restr
             if (j < e) {
                 const int g = ld_stream(indices + j);
                 b = __ldg(gene_bucket + g);
-                if (b >= 0) c = log1pf(ld_stream(counts + j) * scale) * __ldg(gene_weight + g);
+                if (b >= 0) c = xform_value(ld_stream(counts + j), scale) * __ldg(gene_weight + g);
             }
             consume(b, c);
         }
@@ -228,7 +234,7 @@ sketch_contract_v2_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
                           const int32_t *__restrict__ gene_bucket, const float *__restrict__ gene_weight,
                           int d, const float *__restrict__ x_sketch_t, int kp,
                           const int32_t *__restrict__ row_map, const int32_t *__restrict__ row_ids,
-                          float *__restrict__ h, float *__restrict__ ysq)
+                          float *__restrict__ h, float *__restrict__ ysq, int linear)
 {
     constexpr int XR = NK * 32 + 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -272,7 +278,7 @@ sketch_contract_v2_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
                 const int t = t0 + lane;
                 if (t < n) {
                     const int b = list_b[t];
-                    const float c = log1pf(list_v[t] * scale) * list_w[t];
+                    const float c = xform_value(list_v[t], scale) * list_w[t];
                     atomicAdd(acc + b, c);
                     const float4 *xr = reinterpret_cast<const float4 *>(xs + b * XR);
 #pragma unroll
@@ -328,7 +334,7 @@ sketch_contract_v2_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
         int cnt = 0;
         float lib = warp_sum(stream(s, e, cnt, true, 0.f, false));
         if (lib == 0.f) lib = 1.f;
-        const float scale = 1e4f / lib;
+        const float scale = linear ? -1.f : 1e4f / lib;
         __syncwarp();
         if (cnt <= kListCap) {
             flush(cnt, scale);
@@ -375,7 +381,7 @@ sketch_contract_v3_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
                           const int32_t *__restrict__ gene_bucket, const float *__restrict__ gene_weight,
                           int d, const float *__restrict__ x_sketch_t, int kp,
                           const int32_t *__restrict__ row_map, const int32_t *__restrict__ row_ids,
-                          float *__restrict__ h, float *__restrict__ ysq)
+                          float *__restrict__ h, float *__restrict__ ysq, int linear)
 {
     constexpr int XR = NK * 32 + 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -446,7 +452,7 @@ sketch_contract_v3_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
             const int t = t0 + lane;
             if (t < n) {
                 const int2 bw = slot_bw[list_s[t]];
-                const float c = log1pf(list_v[t] * scale) * __int_as_float(bw.y);
+                const float c = xform_value(list_v[t], scale) * __int_as_float(bw.y);
                 atomicAdd(acc + bw.x, c);
                 const float4 *xr = reinterpret_cast<const float4 *>(xs + bw.x * XR);
 #pragma unroll
@@ -543,7 +549,7 @@ sketch_contract_v3_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
         }
         lib = warp_sum(lib);
         if (lib == 0.f) lib = 1.f;
-        const float scale = 1e4f / lib;
+        const float scale = linear ? -1.f : 1e4f / lib;
         const bool overflow = cnt > kListCap;
         // next row's first 512 entries start streaming now and land while this row's AXPY runs
         {
@@ -736,7 +742,7 @@ template <typename IndPtr, int NK>
 static int launch_fused(const void *indptr, const int32_t *indices, const float *counts,
                         int64_t n_spots, int n_genes, int n_selected, const int32_t *gene_bucket,
                         const float *gene_weight, int d, const float *x_sketch_t, int kp, const int32_t *row_map,
-                        const int32_t *row_ids, float *h, float *ysq, cudaStream_t st)
+                        const int32_t *row_ids, float *h, float *ysq, int linear, cudaStream_t st)
 {
     // preferred: v3 (gene->slot and slot->(bucket, weight) tables + compaction lists in shared memory)
     if (n_selected >= 0 && n_selected < 0xFFFF && getenv("FDB_SKETCH_V1") == nullptr && getenv("FDB_SKETCH_V2") == nullptr) {
@@ -752,7 +758,7 @@ static int launch_fused(const void *indptr, const int32_t *indices, const float 
             FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const int grid = pick_grid(n_spots, warps, 1);
             kern<<<grid, warps * 32, smem, st>>>((const IndPtr *)indptr, indices, counts, n_spots, n_genes, n_selected,
-                                                 gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq);
+                                                 gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, linear);
             FDB_LAUNCH_CHECK("sketch_contract_v3_kernel");
             return FDB_OK;
         }
@@ -771,7 +777,7 @@ static int launch_fused(const void *indptr, const int32_t *indices, const float 
             FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const int grid = pick_grid(n_spots, warps, 1);
             kern<<<grid, warps * 32, smem, st>>>((const IndPtr *)indptr, indices, counts, n_spots, n_genes,
-                                                 gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq);
+                                                 gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, linear);
             FDB_LAUNCH_CHECK("sketch_contract_v2_kernel");
             return FDB_OK;
         }
@@ -796,16 +802,15 @@ static int launch_fused(const void *indptr, const int32_t *indices, const float 
     FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = pick_grid(n_spots, warps, per_sm);
     kern<<<grid, warps * 32, smem, st>>>((const IndPtr *)indptr, indices, counts, n_spots, gene_bucket,
-                                         gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq);
+                                         gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, linear);
     FDB_LAUNCH_CHECK("sketch_contract_kernel");
     return FDB_OK;
 }
 
-extern "C" __attribute__((visibility("default"))) int fdb_sketch_contract_csr(const void *indptr, int indptr_is_int64, const int32_t *indices,
-                                       const float *counts, int64_t n_spots, int32_t n_genes,
-                                       const int32_t *gene_bucket, const float *gene_weight, int32_t d,
-                                       const float *x_sketch_t, int32_t n_types, const int32_t *row_map,
-                                       const int32_t *row_ids, int32_t n_selected, float *h, float *ysq, void *stream)
+static int sketch_contract_impl(const void *indptr, int indptr_is_int64, const int32_t *indices, const float *counts,
+                                int64_t n_spots, int32_t n_genes, const int32_t *gene_bucket, const float *gene_weight,
+                                int32_t d, const float *x_sketch_t, int32_t n_types, const int32_t *row_map,
+                                const int32_t *row_ids, int32_t n_selected, float *h, float *ysq, int linear, void *stream)
 {
     FDB_REQUIRE(n_spots >= 0 && n_genes >= 0, "negative shape");
     FDB_REQUIRE(d > 0 && d % 4 == 0, "sketch_dim must be a positive multiple of 4, got %d", d);
@@ -816,11 +821,51 @@ extern "C" __attribute__((visibility("default"))) int fdb_sketch_contract_csr(co
     cudaStream_t st = (cudaStream_t)stream;
     if (kp <= 32)
         return indptr_is_int64
-                   ? launch_fused<int64_t, 1>(indptr, indices, counts, n_spots, n_genes, n_selected, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, st)
-                   : launch_fused<int32_t, 1>(indptr, indices, counts, n_spots, n_genes, n_selected, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, st);
+                   ? launch_fused<int64_t, 1>(indptr, indices, counts, n_spots, n_genes, n_selected, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, linear, st)
+                   : launch_fused<int32_t, 1>(indptr, indices, counts, n_spots, n_genes, n_selected, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, linear, st);
     return indptr_is_int64
-               ? launch_fused<int64_t, 2>(indptr, indices, counts, n_spots, n_genes, n_selected, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, st)
-               : launch_fused<int32_t, 2>(indptr, indices, counts, n_spots, n_genes, n_selected, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, st);
+               ? launch_fused<int64_t, 2>(indptr, indices, counts, n_spots, n_genes, n_selected, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, linear, st)
+               : launch_fused<int32_t, 2>(indptr, indices, counts, n_spots, n_genes, n_selected, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, linear, st);
+}
+
+extern "C" __attribute__((visibility("default"))) int fdb_sketch_contract_csr(const void *indptr, int indptr_is_int64, const int32_t *indices,
+                                       const float *counts, int64_t n_spots, int32_t n_genes,
+                                       const int32_t *gene_bucket, const float *gene_weight, int32_t d,
+                                       const float *x_sketch_t, int32_t n_types, const int32_t *row_map,
+                                       const int32_t *row_ids, int32_t n_selected, float *h, float *ysq, void *stream)
+{
+    return sketch_contract_impl(indptr, indptr_is_int64, indices, counts, n_spots, n_genes, gene_bucket, gene_weight, d,
+                                x_sketch_t, n_types, row_map, row_ids, n_selected, h, ysq, 0, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int fdb_sketch_linear_contract_csr(const void *indptr, int indptr_is_int64, const int32_t *indices,
+                                       const float *counts, int64_t n_spots, int32_t n_genes,
+                                       const int32_t *gene_bucket, const float *gene_weight, int32_t d,
+                                       const float *x_sketch_t, int32_t n_types, const int32_t *row_map,
+                                       const int32_t *row_ids, int32_t n_selected, float *h, float *ysq, void *stream)
+{
+    return sketch_contract_impl(indptr, indptr_is_int64, indices, counts, n_spots, n_genes, gene_bucket, gene_weight, d,
+                                x_sketch_t, n_types, row_map, row_ids, n_selected, h, ysq, 1, stream);
+}
+
+// per-gene sums of the raw counts (float64), for the per-gene scale of preprocess "pearson" (core/deconv.py:206-212)
+__global__ void __launch_bounds__(256)
+gene_sums_kernel(const int32_t *__restrict__ indices, const float *__restrict__ counts, int64_t nnz, double *__restrict__ sums)
+{
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nnz; j += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(sums + ld_stream(indices + j), (double)ld_stream(counts + j));
+}
+
+extern "C" __attribute__((visibility("default"))) int fdb_gene_sums_csr(const int32_t *indices, const float *counts, int64_t nnz, int32_t n_genes,
+                                 double *sums, void *stream)
+{
+    FDB_REQUIRE(nnz >= 0 && n_genes >= 0, "negative shape");
+    if (nnz == 0) return FDB_OK;
+    FDB_REQUIRE(indices && counts && sums, "null pointer");
+    const int grid = (int)std::min<int64_t>(ceil_div(nnz, 256), (int64_t)kNumSM * 16);
+    gene_sums_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(indices, counts, nnz, sums);
+    FDB_LAUNCH_CHECK("gene_sums_kernel");
+    return FDB_OK;
 }
 
 extern "C" __attribute__((visibility("default"))) int fdb_gene_moments_csr(const void *indptr, int indptr_is_int64, const int32_t *indices,

@@ -2,8 +2,9 @@
 
 Same constructor, validation messages, methods and fitted attributes as the
 reference class; steps 2-6 of ``fit`` run on the GPU through libfdb200 (there is
-no CPU fallback).  ``preprocess`` values other than "log_cpm" are outside the
-accelerated path and raise NotImplementedError.
+no CPU fallback).  All three ``preprocess`` values run on the device: "log_cpm"
+transforms values inside the fused sketch kernel; "raw" and "pearson" are per-gene
+scalings folded into the device-side gene weights (core/deconv.py:199-229).
 """
 from __future__ import annotations
 
@@ -82,9 +83,6 @@ class FlashDeconv:
         if self.preprocess not in ("log_cpm", "pearson", "raw"):
             raise ValueError(f"Unknown preprocess method: {self.preprocess}. "
                              "Choose from 'log_cpm', 'pearson', or 'raw'.")
-        if self.preprocess != "log_cpm":
-            raise NotImplementedError(f"preprocess='{self.preprocess}' is outside the B200 hot path "
-                                      "(only 'log_cpm' is accelerated); see DESIGN.md, out of scope.")
         from . import pipeline        # imports the native library: fails loudly when it is missing
 
         say = print if self.verbose else (lambda *a, **k: None)
@@ -104,13 +102,14 @@ class FlashDeconv:
                                                                    n_markers_per_type=self.n_markers_per_type)
         self.gene_idx_ = gene_idx
         say(f"  Selected {len(gene_idx)} genes (HVG + markers)")
-        say(f"Step 2-3: log-CPM + sketching to {self.sketch_dim} dimensions (fused, on device)...")
+        say(f"Step 2-3: {self.preprocess} preprocessing + sketching to {self.sketch_dim} dimensions (fused, on device)...")
         say("Step 4-6: spatial graph, lambda, block coordinate descent...")
         res = pipeline.deconvolve_path(csr, X, coords, gene_idx, leverage, sketch_dim=self.sketch_dim,
                                        lambda_spatial=self.lambda_spatial, rho_sparsity=self.rho_sparsity,
                                        spatial_method=self.spatial_method, k_neighbors=self.k_neighbors,
                                        radius=self.radius, max_iter=self.max_iter, tol=self.tol,
-                                       random_state=self.random_state, verbose=self.verbose)
+                                       random_state=self.random_state, verbose=self.verbose,
+                                       preprocess=self.preprocess)
         self._graph, self._adjacency = res.graph, None
         self.lambda_used_ = res.lambda_used
         self.beta_, self.proportions_, self.info_ = res.beta, res.proportions, res.info

@@ -93,6 +93,7 @@ class SketchTables:
     X_sketch: np.ndarray         # float64 K x d
     gram: np.ndarray             # float64 K x K
     d: int
+    linear: bool = False         # preprocess "raw" / "pearson": value = count * per-gene factor (no log-CPM)
 
 
 def countsketch_table(n_genes: int, d: int, leverage, seed):
@@ -120,20 +121,41 @@ def countsketch_table(n_genes: int, d: int, leverage, seed):
     return bucket.astype(np.int64), sign.astype(np.int64), weight
 
 
-def build_tables(X, gene_idx, leverage, d, seed, n_genes_total) -> SketchTables:
-    """Everything about the reference side that stays on the host (K x G_sel work)."""
+PEARSON_THETA = 100.0            # core/deconv.py:203
+
+
+def build_tables(X, gene_idx, leverage, d, seed, n_genes_total, preprocess="log_cpm", y_col_mean=None) -> SketchTables:
+    """Everything about the reference side that stays on the host (K x G_sel work).
+
+    preprocess follows FlashDeconv._preprocess_data (core/deconv.py:177-235): "log_cpm" transforms values on the
+    device; "raw" and "pearson" scale every gene column by a constant (1, or 1 / sigma_g with sigma_g^2 = mu_g +
+    mu_g^2 / theta, mu_g = mean over spots + 1e-6 -- `y_col_mean` holds the means of ALL input genes), which is
+    folded into the device-side gene weights."""
     X = np.asarray(X, dtype=np.float64)
     gene_idx = np.asarray(gene_idx, dtype=np.intp)
     bucket, sign, weight = countsketch_table(len(gene_idx), d, leverage, seed)
     Xsel = X[:, gene_idx]
-    Xt = np.log1p(Xsel / (Xsel.sum(axis=1, keepdims=True) + 1e-10) * 1e4)      # core/deconv.py:194-195
+    factor = np.ones(len(gene_idx))
+    if preprocess == "log_cpm":
+        Xt = np.log1p(Xsel / (Xsel.sum(axis=1, keepdims=True) + 1e-10) * 1e4)  # core/deconv.py:194-195
+    elif preprocess == "raw":
+        Xt = Xsel                                                               # core/deconv.py:227-229
+    elif preprocess == "pearson":                                               # core/deconv.py:199-225
+        if y_col_mean is None:
+            raise ValueError("preprocess='pearson' needs the per-gene means of Y")
+        mu_y = np.asarray(y_col_mean, dtype=np.float64)[gene_idx] + 1e-6
+        factor = 1.0 / np.sqrt(mu_y + mu_y ** 2 / PEARSON_THETA)
+        mu_x = Xsel.mean(axis=0, keepdims=True) + 1e-6
+        Xt = Xsel / np.sqrt(mu_x + mu_x ** 2 / PEARSON_THETA)
+    else:
+        raise ValueError(f"Unknown preprocess method: {preprocess}. Choose from 'log_cpm', 'pearson', or 'raw'.")
     Xs = np.zeros((X.shape[0], d))
     np.add.at(Xs.T, bucket, (Xt * weight).T)                                   # X~ @ Omega, core/sketching.py:202
     gb = np.full(n_genes_total, -1, dtype=np.int32)
     gw = np.zeros(n_genes_total, dtype=np.float32)
     gb[gene_idx] = bucket
-    gw[gene_idx] = weight
-    return SketchTables(gb, gw, bucket, sign, weight, Xs, Xs @ Xs.T, d)
+    gw[gene_idx] = weight * factor
+    return SketchTables(gb, gw, bucket, sign, weight, Xs, Xs @ Xs.T, d, linear=preprocess != "log_cpm")
 
 
 @dataclass
@@ -253,11 +275,10 @@ class DevicePath:
         """Fused log-CPM + CountSketch + contraction; rows land in tile order (needs the graph)."""
         c, tb = self.csr, self.tables
         row_map = self.graph.rank if self.graph is not None else None
-        check(lib.fdb_sketch_contract_csr(_ptr(c.indptr), int(c.indptr.dtype == self.torch.int64), _ptr(c.indices),
-                                          _ptr(c.data), c.shape[0], c.shape[1], _ptr(self.gene_bucket),
-                                          _ptr(self.gene_weight), tb.d, _ptr(self.x_sketch_t), self.K,
-                                          _ptr(row_map), _ptr(None), int(len(tb.bucket)), _ptr(self.h), _ptr(self.ysq),
-                                          _stream(self.torch)),
+        fn = lib.fdb_sketch_linear_contract_csr if tb.linear else lib.fdb_sketch_contract_csr
+        check(fn(_ptr(c.indptr), int(c.indptr.dtype == self.torch.int64), _ptr(c.indices), _ptr(c.data), c.shape[0],
+                 c.shape[1], _ptr(self.gene_bucket), _ptr(self.gene_weight), tb.d, _ptr(self.x_sketch_t), self.K,
+                 _ptr(row_map), _ptr(None), int(len(tb.bucket)), _ptr(self.h), _ptr(self.ysq), _stream(self.torch)),
               "sketch_contract_csr")
 
     def lambda_auto(self, alpha=0.005) -> float:
@@ -407,15 +428,26 @@ def gene_moments(csr: DeviceCSR):
     return sums.cpu().numpy(), sq.cpu().numpy()
 
 
+def gene_col_means(csr: DeviceCSR) -> np.ndarray:
+    """Per-gene mean of the raw counts over all spots (Y.mean(axis=0), core/deconv.py:207) -> host float64."""
+    torch = _native.require_cuda()
+    G = csr.shape[1]
+    sums = torch.zeros(G, dtype=torch.float64, device=csr.indices.device)
+    nnz = int(csr.indices.numel())
+    check(lib.fdb_gene_sums_csr(_ptr(csr.indices), _ptr(csr.data), nnz, G, _ptr(sums), _stream(torch)), "gene_sums_csr")
+    return sums.cpu().numpy() / max(csr.shape[0], 1)
+
+
 def deconvolve_path(Y, X, coords, gene_idx, leverage, *, sketch_dim=512, lambda_spatial="auto", rho_sparsity=0.01,
                     spatial_method="knn", k_neighbors=6, radius=None, max_iter=100, tol=1e-4, random_state=0,
-                    verbose=False, pinned_out=False) -> SolveResult:
+                    verbose=False, pinned_out=False, preprocess="log_cpm") -> SolveResult:
     """Steps 2-6 of FlashDeconv.fit for HOST inputs (scipy CSR / ndarray counts, ndarray coords): uploads,
     runs the device path, downloads float64 beta / proportions in input order.  This is the call
     `FlashDeconv.fit` makes after gene selection and the one bench.py times end to end."""
     torch = _native.require_cuda()
-    tables = build_tables(X, gene_idx, leverage, sketch_dim, random_state, Y.shape[1])
     csr = csr_to_device(Y)
+    y_mean = gene_col_means(csr) if preprocess == "pearson" else None
+    tables = build_tables(X, gene_idx, leverage, sketch_dim, random_state, Y.shape[1], preprocess, y_mean)
     c = coords if torch.is_tensor(coords) else torch.from_numpy(np.ascontiguousarray(coords, dtype=np.float64))
     coords_dev = c.to(csr.indices.device, non_blocking=True)
     path = DevicePath(csr, coords_dev, tables, np.asarray(X).shape[0])

@@ -87,6 +87,21 @@ int fdb_sketch_contract_csr(const void *indptr, int indptr_is_int64, const int32
                             const float *x_sketch_t, int32_t n_types, const int32_t *row_map,
                             const int32_t *row_ids, int32_t n_selected, float *h, float *ysq, void *stream);
 
+/* The same pass for FlashDeconv._preprocess_data's LINEAR branches, "raw" (core/deconv.py:227-229) and "pearson"
+ * (:199-225): the preprocessed value of an entry is count * f_g with a per-gene factor f_g (1, or 1 / sigma_g with
+ * sigma_g^2 = mu_g + mu_g^2 / 100, mu_g = column mean + 1e-6), which the caller folds into gene_weight; no library
+ * size, no log1p.  Same arguments and outputs as fdb_sketch_contract_csr. */
+int fdb_sketch_linear_contract_csr(const void *indptr, int indptr_is_int64, const int32_t *indices,
+                                   const float *counts, int64_t n_spots, int32_t n_genes,
+                                   const int32_t *gene_bucket, const float *gene_weight, int32_t d,
+                                   const float *x_sketch_t, int32_t n_types, const int32_t *row_map,
+                                   const int32_t *row_ids, int32_t n_selected, float *h, float *ysq, void *stream);
+
+/* Per-gene sums of the raw counts, float64, ACCUMULATED into sums[n_genes] (zero it first): the column means of
+ * preprocess "pearson" (Y.mean(axis=0), core/deconv.py:207). */
+int fdb_gene_sums_csr(const int32_t *indices, const float *counts, int64_t nnz, int32_t n_genes, double *sums,
+                      void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * (a5) spatial graph.  Replaces build_knn_graph (utils/graph.py:25-83), build_radius_graph
  * (:86-133) and build_grid_graph (:136-172): float64 squared distances, k nearest OTHER

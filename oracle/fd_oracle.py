@@ -181,6 +181,25 @@ def log_cpm(Y_sel, X_sel):
     return Yt, Xt
 
 
+# f2: the linear preprocess branches -- core/deconv.py:199-229
+def preprocess(Y_sel, X_sel, method="log_cpm"):
+    if method == "log_cpm":
+        return log_cpm(Y_sel, X_sel)
+    if method == "raw":
+        return Y_sel.astype(np.float64, copy=False), X_sel.astype(np.float64, copy=False)
+    if method == "pearson":
+        theta = 100.0
+        if sparse.issparse(Y_sel):
+            mu = np.asarray(Y_sel.mean(axis=0)).flatten() + 1e-6
+            Yt = Y_sel.multiply(1.0 / np.sqrt(mu + mu ** 2 / theta))
+        else:
+            mu = Y_sel.mean(axis=0, keepdims=True) + 1e-6
+            Yt = Y_sel / np.sqrt(mu + mu ** 2 / theta)
+        mx = X_sel.mean(axis=0, keepdims=True) + 1e-6
+        return Yt, X_sel / np.sqrt(mx + mx ** 2 / theta)
+    raise ValueError(f"Unknown preprocess method: {method}. Choose from 'log_cpm', 'pearson', or 'raw'.")
+
+
 # --------------------------------------------------------------------------
 # a2: CountSketch table -- core/sketching.py:48-84
 # --------------------------------------------------------------------------
@@ -400,7 +419,7 @@ def bcd_solve(Y_s, X_s, A, lam=0.1, rho=0.01, max_iter=100, tol=1e-4, trace=None
 # whole path, stage by stage (FlashDeconv.fit steps 2-6, core/deconv.py:321-398)
 # --------------------------------------------------------------------------
 def run_path(Y, X, coords, gene_idx, leverage, *, d=512, lam="auto", rho=0.01, method="knn",
-             k=6, radius=None, max_iter=100, tol=1e-4, seed=0, timings=None):
+             k=6, radius=None, max_iter=100, tol=1e-4, seed=0, timings=None, preprocess_method="log_cpm"):
     import time
     t = time.perf_counter
     t0 = t()
@@ -409,7 +428,9 @@ def run_path(Y, X, coords, gene_idx, leverage, *, d=512, lam="auto", rho=0.01, m
         Ysel = Ysel.tocsr()
     Xsel = X[:, gene_idx]
     t1 = t()
-    Yt, Xt = log_cpm(Ysel, Xsel)
+    Yt, Xt = preprocess(Ysel, Xsel, preprocess_method)
+    if sparse.issparse(Yt):
+        Yt = Yt.tocsr()
     t2 = t()
     bucket, sign, weight = countsketch_table(len(gene_idx), d, leverage, seed)
     Ys, Xs = project(Yt, Xt, omega_matrix(bucket, weight, d))

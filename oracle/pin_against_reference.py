@@ -52,7 +52,8 @@ def rel(a, b):
 
 
 def pin_path_case(name, *, n_spots, n_genes, n_types, depth, d, k=6, method="knn", seed=0,
-                  dense=False, jitter=0.1, max_iter=100, n_hvg=2000, n_markers=50, keep_rows=None):
+                  dense=False, jitter=0.1, max_iter=100, n_hvg=2000, n_markers=50, keep_rows=None,
+                  preprocess="log_cpm"):
     ds = make_dataset(n_spots=n_spots, n_genes=n_genes, n_types=n_types, depth=depth,
                       jitter=jitter, seed=seed)
     Y = ds.Y.toarray().astype(np.float64) if dense else ds.Y.astype(np.float64)   # float64 counts: the reference's sparse log-CPM keeps the input dtype (deconv.py:183-188)
@@ -61,11 +62,11 @@ def pin_path_case(name, *, n_spots, n_genes, n_types, depth, d, k=6, method="knn
     # ---- reference, stage by stage (mirrors FlashDeconv.fit) ----
     gene_idx, lev = select_informative_genes(Y, X, n_hvg=n_hvg, n_markers_per_type=n_markers)
     model = RefFlashDeconv(sketch_dim=d, k_neighbors=k, spatial_method=method, max_iter=max_iter,
-                           n_hvg=n_hvg, n_markers_per_type=n_markers, random_state=seed)
+                           n_hvg=n_hvg, n_markers_per_type=n_markers, random_state=seed, preprocess=preprocess)
     Ysub = Y[:, gene_idx]
     if sparse.issparse(Ysub):
         Ysub = Ysub.tocsr()
-    Yt, Xt = model._preprocess_data(Ysub, X[:, gene_idx], "log_cpm")
+    Yt, Xt = model._preprocess_data(Ysub, X[:, gene_idx], preprocess)
     Ys, Xs, Omega = sketch_data(Yt, Xt, sketch_dim=d, leverage_scores=lev, random_state=seed)
     Omega = Omega.tocsr()
     A = coords_to_adjacency(coords, method=method, k=k)
@@ -75,14 +76,15 @@ def pin_path_case(name, *, n_spots, n_genes, n_types, depth, d, k=6, method="knn
     prop = normalize_proportions(beta)
     # end-to-end through the public class must agree with the staged run
     full = RefFlashDeconv(sketch_dim=d, k_neighbors=k, spatial_method=method, max_iter=max_iter,
-                          n_hvg=n_hvg, n_markers_per_type=n_markers, random_state=seed)
+                          n_hvg=n_hvg, n_markers_per_type=n_markers, random_state=seed, preprocess=preprocess)
     assert np.array_equal(full.fit_transform(Y, X, coords), prop)
 
     # ---- oracle on the same inputs ----
     o_idx, o_lev = fo.select_genes(Y, X, n_hvg, n_markers)
     assert np.array_equal(o_idx, gene_idx), name
     assert rel(o_lev, lev) < 1e-9, (name, rel(o_lev, lev))
-    res = fo.run_path(Y, X, coords, gene_idx, lev, d=d, method=method, k=k, max_iter=max_iter, seed=seed)
+    res = fo.run_path(Y, X, coords, gene_idx, lev, d=d, method=method, k=k, max_iter=max_iter, seed=seed,
+                      preprocess_method=preprocess)
     ref_bucket = Omega.indices.copy()
     ref_w = Omega.data.copy()
     assert Omega.nnz == len(gene_idx) and np.all(np.diff(Omega.indptr) == 1)
@@ -99,7 +101,7 @@ def pin_path_case(name, *, n_spots, n_genes, n_types, depth, d, k=6, method="knn
     assert rel(res["beta"], beta) < 1e-9, (name, rel(res["beta"], beta))
     assert rel(res["proportions"], prop) < 1e-9
     assert abs(res["info"]["final_objective"] - info["final_objective"]) <= 1e-9 * abs(info["final_objective"])
-    if sparse.issparse(Y):          # the fused full-CSR formulation the CUDA kernel uses
+    if sparse.issparse(Y) and preprocess == "log_cpm":      # the fused full-CSR formulation the CUDA kernel uses
         Yf = fo.sketch_full_csr(Y, gene_idx, res["bucket"], res["weight"], d)
         assert rel(Yf, Ys) < 1e-12, (name, rel(Yf, Ys))
     # tie-freeness of the k/(k+1) boundary (precondition for bit-exact kNN sets)
@@ -120,6 +122,7 @@ def pin_path_case(name, *, n_spots, n_genes, n_types, depth, d, k=6, method="knn
         converged=np.array(info["converged"]), final_objective=np.array(info["final_objective"]),
         final_change=np.array(info["final_change"]),
         params=np.array([d, k, seed, max_iter, n_hvg, n_markers]), method=np.array(method),
+        preprocess=np.array(preprocess),
         versions=np.array(repr(VERSIONS)))
     print(f"[pin] {name}: N={n_spots} G={n_genes}->{len(gene_idx)} K={n_types} d={d} nnz(A)={A.nnz} "
           f"iters={info['n_iterations']} conv={info['converged']} lam={lam:.5g} OK")
@@ -188,4 +191,8 @@ if __name__ == "__main__":
                   keep_rows=25)
     pin_path_case("path_grid", n_spots=900, n_genes=700, n_types=8, depth=500.0, d=128, seed=3,
                   method="grid", jitter=0.0)
+    # the linear preprocess branches (core/deconv.py:199-229), "next" row f2
+    pin_path_case("path_raw", n_spots=500, n_genes=800, n_types=7, depth=300.0, d=64, seed=4, preprocess="raw")
+    pin_path_case("path_pearson", n_spots=700, n_genes=900, n_types=10, depth=350.0, d=128, seed=5,
+                  preprocess="pearson")
     print("all pins OK; versions:", VERSIONS)

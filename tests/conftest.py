@@ -51,6 +51,7 @@ class Golden:
         self.final_objective, self.final_change = float(z["final_objective"]), float(z["final_change"])
         self.d, self.k, self.seed, self.max_iter, self.n_hvg, self.n_markers = (int(v) for v in z["params"])
         self.method = str(z["method"])
+        self.preprocess = str(z["preprocess"]) if "preprocess" in z.files else "log_cpm"
 
     def Y_input(self):
         return self.Y.toarray() if self.dense_input else self.Y
@@ -59,8 +60,16 @@ class Golden:
 PATH_CASES = ["path_sparse_small", "path_dense_small", "path_sparse_k30", "path_grid"]
 
 
+LINEAR_CASES = ["path_raw", "path_pearson"]          # preprocess="raw" / "pearson" (core/deconv.py:199-229)
+
+
 @pytest.fixture(params=PATH_CASES)
 def golden(request):
+    return Golden(request.param)
+
+
+@pytest.fixture(params=LINEAR_CASES)
+def golden_linear(request):
     return Golden(request.param)
 
 

@@ -347,6 +347,23 @@ def test_fit_transform_matches_reference(golden):
     assert m.summary()["fitted"] and m.get_dominant_cell_type().shape == (golden.Y.shape[0],)
 
 
+def test_fit_transform_linear_preprocess_matches_reference(golden_linear):
+    """preprocess='raw' / 'pearson' (core/deconv.py:199-229, "next" row f2): the per-gene factor is folded into the
+    device-side gene weights and the fused kernel runs without log-CPM.  Both cases converge before max_iter, so this
+    also holds the device-side stop test to the reference's sweep count (+-1: the float32 change ratio crosses tol
+    within one sweep of the float64 one)."""
+    from flashdeconv_b200 import FlashDeconv
+    g = golden_linear
+    m = FlashDeconv(sketch_dim=g.d, k_neighbors=g.k, spatial_method=g.method, max_iter=g.max_iter, n_hvg=g.n_hvg,
+                    n_markers_per_type=g.n_markers, random_state=g.seed, preprocess=g.preprocess)
+    prop = m.fit_transform(g.Y_input(), g.X, g.coords)
+    assert np.array_equal(m.gene_idx_, g.gene_idx)
+    assert m.info_["converged"] and g.converged and abs(m.info_["n_iterations"] - g.n_iterations) <= 1
+    check_props(prop, g.proportions)
+    assert abs(m.lambda_used_ - g.lam) <= 1e-6 * g.lam
+    assert abs(m.info_["final_objective"] - g.final_objective) <= 1e-4 * abs(g.final_objective)
+
+
 def test_fit_variants_behave_like_the_reference_tests():
     """tests/test_integration.py:117-271: sparse==dense input, seeds, sketch dims, radius/grid methods"""
     from flashdeconv_b200 import FlashDeconv

@@ -23,6 +23,18 @@ def test_oracle_gene_selection_matches_reference(golden):
     assert rel(lev, golden.leverage) < 1e-9
 
 
+def test_oracle_linear_preprocess_matches_reference(golden_linear):
+    """preprocess='raw' / 'pearson' (core/deconv.py:199-229): whole path against the reference's outputs; these
+    cases CONVERGE (15 / 27 sweeps), so the stop test (core/solver.py:395-413) is pinned too"""
+    g = golden_linear
+    res = fo.run_path(g.Y_input(), g.X, g.coords, g.gene_idx, g.leverage, d=g.d, method=g.method, k=g.k,
+                      max_iter=g.max_iter, seed=g.seed, preprocess_method=g.preprocess)
+    assert g.converged and res["info"]["converged"] and res["info"]["n_iterations"] == g.n_iterations < g.max_iter
+    assert rel(res["Y_s"][g.Ys_rows], g.Ys) < 1e-12 and rel(res["X_s"], g.Xs) < 1e-12
+    assert rel(res["proportions"], g.proportions) < 1e-9 and rel(res["beta"], g.beta) < 1e-9
+    assert abs(res["lam"] - g.lam) <= 1e-12 * g.lam
+
+
 def test_oracle_countsketch_bit_exact(golden):
     bucket, sign, weight = fo.countsketch_table(len(golden.gene_idx), golden.d, golden.leverage, golden.seed)
     assert np.array_equal(bucket, golden.bucket)
