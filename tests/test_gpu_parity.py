@@ -300,6 +300,34 @@ def test_bcd_all_type_counts_vs_oracle(fo, K):
     assert abs(info["final_objective"] - winfo["final_objective"]) <= 1e-4 * abs(winfo["final_objective"]) + 1e-3
 
 
+@pytest.mark.parametrize("K,graph", [(2, "knn"), (8, "knn"), (11, "knn"), (16, "knn"), (23, "knn"), (26, "dense"),
+                                     (30, "knn"), (32, "knn"), (37, "knn"), (44, "knn"), (50, "dense"), (57, "knn"),
+                                     (64, "knn")])
+def test_bcd_weak_coupling_all_row_widths_vs_oracle(fo, K, graph):
+    """the PRODUCTION sweep kernel (weak coupling -> fp16 gather tile, persistent, pair-step descent) for every row
+    width Kp and every compiled-out padding count; "dense" = a radius graph with ~40 neighbours per spot: more than
+    16 per row (CSR-order codes instead of the transposed byte blocks) and more foreign rows than the 126 halo
+    slots of a patch (fp32 rows fetched from global)"""
+    from flashdeconv_b200.solver import bcd_solve
+    rng = np.random.default_rng(100 + K)
+    n, d = 1500, 96
+    Xs = rng.standard_normal((K, d)) + 0.3
+    bt = rng.random((n, K)) * (rng.random((n, K)) < 0.4)
+    Ys = bt @ Xs + 0.05 * rng.standard_normal((n, d))
+    coords = rng.random((n, 2))
+    A = fo.knn_adjacency(coords, 6) if graph == "knn" else fo.radius_adjacency(coords, 0.095)
+    if graph == "dense":
+        assert np.diff(A.indptr).max() > 16 and np.diff(A.indptr).mean() > 30
+    lam = 0.02                                                   # lam * 8 << 2 % of mean(diag G): fp16 gather admissible
+    assert lam * 8 <= 0.02 * np.mean(np.sum(Xs * Xs, axis=1))
+    want, winfo = fo.bcd_solve(Ys, Xs, A, lam, 0.01, 8, 1e-12)
+    got, info = bcd_solve(Ys, Xs, A, lambda_=lam, rho=0.01, max_iter=8, tol=1e-12)
+    # (a tiny K can reach an exact float32 fixed point -- change 0 -- before the float64 oracle stops moving)
+    assert winfo["n_iterations"] == 8 and (info["n_iterations"] == 8 or info["final_change"] == 0.0)
+    assert np.max(np.abs(got - want)) <= 2e-4 * max(1.0, np.abs(want).max())
+    assert abs(info["final_objective"] - winfo["final_objective"]) <= 1e-4 * abs(winfo["final_objective"]) + 1e-3
+
+
 def test_bcd_edge_cases():
     from flashdeconv_b200.solver import bcd_solve, normalize_proportions, compute_objective
     from flashdeconv_b200.spatial import compute_laplacian
