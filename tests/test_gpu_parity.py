@@ -322,8 +322,9 @@ def test_bcd_weak_coupling_all_row_widths_vs_oracle(fo, K, graph):
     assert lam * 8 <= 0.02 * np.mean(np.sum(Xs * Xs, axis=1))
     want, winfo = fo.bcd_solve(Ys, Xs, A, lam, 0.01, 8, 1e-12)
     got, info = bcd_solve(Ys, Xs, A, lambda_=lam, rho=0.01, max_iter=8, tol=1e-12)
-    # (a tiny K can reach an exact float32 fixed point -- change 0 -- before the float64 oracle stops moving)
-    assert winfo["n_iterations"] == 8 and (info["n_iterations"] == 8 or info["final_change"] == 0.0)
+    # (a tiny K can reach an exact fixed point -- change 0 -- within the 8 sweeps, in float32 possibly a sweep or two
+    # before the float64 oracle does)
+    assert info["n_iterations"] == winfo["n_iterations"] or info["final_change"] == 0.0, (info, winfo)
     assert np.max(np.abs(got - want)) <= 2e-4 * max(1.0, np.abs(want).max())
     assert abs(info["final_objective"] - winfo["final_objective"]) <= 1e-4 * abs(winfo["final_objective"]) + 1e-3
 
