@@ -414,8 +414,12 @@ def test_fit_variants_behave_like_the_reference_tests():
         np.testing.assert_allclose(m.proportions_.sum(1), 1.0, atol=1e-9)
     m = FlashDeconv(sketch_dim=64, lambda_spatial=0.5, max_iter=5).fit(Yd, ds.X, ds.coords)
     assert m.lambda_used_ == 0.5 and m.info_["n_iterations"] == 5
-    with pytest.raises(NotImplementedError):
-        FlashDeconv(preprocess="pearson").fit(Yd, ds.X, ds.coords)
+    for pp in ("pearson", "raw"):                               # tests/test_integration.py:238-257
+        m = FlashDeconv(sketch_dim=64, max_iter=20, preprocess=pp).fit(Yd, ds.X, ds.coords)
+        assert m.proportions_.shape == (100, 5) and np.all(m.proportions_ >= 0)
+        np.testing.assert_allclose(m.proportions_.sum(1), 1.0, atol=1e-9)
+    with pytest.raises(ValueError, match="Unknown preprocess method"):
+        FlashDeconv(preprocess="bogus").fit(Yd, ds.X, ds.coords)
 
 
 # ---------------------------------------------------------------- multi-GPU tiling
