@@ -9,26 +9,27 @@
 //   core/solver.py:395-413  rel = max|delta| / (max|old| + 1e-10); stop when rel < tol
 //   core/solver.py:269-284  objective;  core/solver.py:445-452 normalisation
 //
-// Sweep kernel mapping (HBM-bound: (12*Kp + 4*deg + 4) bytes per spot per sweep):
-//   CTA = 4 independent warps, each owning 32 consecutive spots (tile order, so neighbours are
-//   nearby in memory).
-//   phase A (coalesced): groups of Kp/4 lanes stream whole 16B-aligned rows -- the spot's H row,
-//     its beta row and its neighbours' beta rows -- and leave c = H + lam * nsum and beta_old in
-//     shared memory.
-//   phase B (thread per spot): the K-step coordinate descent is strictly sequential per spot, so
-//     each lane runs one spot with its beta row in registers and evaluates the partial residual
-//     in the direct form part_k = c_k - sum_{j!=k} G_kj b_j (K^2 FMAs per spot, the dense minimum;
-//     the reference's maintained-residual form costs 1.5-2 K^2 under SIMT).  The Gram matrix is a
-//     by-value kernel parameter: every FFMA takes its G operand from the constant bank.
-//   phase C (coalesced): the warp streams its 32 new rows back out.
-//   Convergence statistics: redux.sync max per warp, one atomicMax per CTA, last CTA finalises.
+// What lives where (HBM-bound: (12*Kp + 4*deg + 4) bytes per spot per sweep):
+//   bcd_p.cuh / bcd_p_inst.cu   the PRODUCTION sweep kernel bcd_sweep_p_kernel (persistent, software-pipelined over
+//                               128-spot patches, fp16 gather tile, pair-step descent), one translation unit per Kp
+//   this file                   bcd_sweep_kernel: fp32-gather sweep, one patch per CTA -- the fallback when the spatial
+//                               coupling is strong (fp16 neighbour values inadmissible) or no gather plan is given;
+//                               bcd_plan_kernel: per-patch halo lists and neighbour codes, built once per graph;
+//                               bcd_sweep_h_kernel / bcd_sweep_d_kernel: comparison kernels (FDB_SWEEP_VARIANT=4 / 6,
+//                               Kp = 32 only: one patch per CTA; persistent with two spots per lane);
+//                               dispatcher, objective terms (float64 accumulation), proportions, C entry points.
+//   Common to all sweep kernels: thread per spot for the strictly sequential K-step coordinate descent, evaluated in
+//   the direct form part_k = c_k - sum_{j!=k} G_kj b_j (K^2 FMAs per spot, the dense minimum; the reference's
+//   maintained-residual form costs 1.5-2 K^2 under SIMT) on packed fma.rn.f32x2 with the negated Gram matrix as a
+//   by-value kernel parameter (constant bank); coalesced row traffic staged through shared memory; convergence
+//   statistics by redux.sync max per warp, one atomicMax per CTA, last CTA finalises the stop test.
 #include "bcd_common.cuh"
 
 extern "C" __attribute__((visibility("default"))) int fdb_bcd_init(float *beta, int64_t n_rows, int32_t n_types, void *state, void *stream);
 
 namespace fdb {
 
-// Sweep kernel, tile-cached form (production).  One CTA = NW warps = TILE = 32*NW consecutive spots
+// Sweep kernel, tile-cached fp32-gather form (fallback: strong coupling / no plan).  One CTA = NW warps = TILE = 32*NW consecutive spots
 // (tile order => a compact patch of the tissue).
 //   step 1  the CTA streams its TILE beta_old rows and H rows into shared memory with fully
 //           independent coalesced 128-bit loads (one global round trip, 2*Kp/4 loads in flight per thread);
@@ -203,7 +204,8 @@ bcd_sweep_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP
 }
 
 // ------------------------------------------------------------------------------------
-// Sweep kernel, halo-staged form with a half-precision gather tile (production for Kp % 8 == 0).
+// Sweep kernel, halo-staged form with a half-precision gather tile, one patch per CTA (comparison kernel,
+// FDB_SWEEP_VARIANT=4, Kp = 32; the production kernel in bcd_p.cuh keeps its gather tile and adds the pipeline).
 //
 // Same four steps as bcd_sweep_kernel, with the neighbour gather made a pure shared-memory operation:
 //   * the CTA's TILE beta_old rows are staged twice: fp32 (own rows, needed exactly by the descent) and as an
@@ -515,7 +517,8 @@ bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<
 }
 
 // ------------------------------------------------------------------------------------
-// Sweep kernel, persistent pipelined form with TWO spots per lane (production for Kp % 8 == 0).
+// Sweep kernel, persistent pipelined form with TWO spots per lane (comparison kernel, FDB_SWEEP_VARIANT=6, Kp = 32:
+// 18 % fewer instructions than the production kernel but 12 warps/SM; measured 122 vs 99 us per sweep at C3).
 //
 // Same pipeline as bcd_sweep_p_kernel (scalars, codes and rows of patch p+1 requested while p is computed), but
 // a CTA is 2 warps = 64 lanes for a 128-spot patch and lane l of warp w owns spots a = 64 w + l and b = a + 32.

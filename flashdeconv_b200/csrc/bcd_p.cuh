@@ -7,7 +7,7 @@
 namespace fdb {
 
 // ------------------------------------------------------------------------------------
-// Sweep kernel, persistent software-pipelined form (production for Kp % 8 == 0).
+// Sweep kernel, persistent software-pipelined form (production; every K, rows padded to Kp = 8 ceil(K / 8)).
 //
 // bcd_sweep_h_kernel runs one patch per CTA, and because every CTA of a wave takes the same time the waves stay
 // in lock-step: all resident CTAs wait on their start-of-patch DRAM round trips together (37 % of the warp time

@@ -194,7 +194,7 @@ sketch_contract_kernel(const IndPtr *__restrict__ indptr, const int32_t *__restr
 }
 
 // ------------------------------------------------------------------------------------
-// fused form, v2 (production): same result as sketch_contract_kernel with ~5x fewer instructions.
+// fused form, v2 (fallback when the selected-gene count is unknown or the tables do not fit): same result as sketch_contract_kernel with ~5x fewer instructions.
 //   * per-gene bucket table lives in shared memory as u16 (0xFFFF = gene not selected), so the
 //     82 % of non-zeros that belong to unselected genes cost one LDS and no global lookup;
 //   * pass 1 streams the row, sums the library size and COMPACTS the selected entries
