@@ -49,9 +49,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         common += ["-Xptxas", "-v"]
 
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers += [os.path.join(os.path.dirname(HERE), "include", "fdb200.h"), os.path.abspath(__file__)]
+    newest_header = max(os.path.getmtime(h) for h in headers)
+
     def one(job):
         src, defs, tag = job
         obj = os.path.join(OBJ, src.replace(".cu", tag + ".o"))
+        # incremental: an object is reused while it is newer than its source and every header
+        if (not force and not verbose and os.path.exists(obj)
+                and os.path.getmtime(obj) > max(newest_header, os.path.getmtime(os.path.join(CSRC, src)))):
+            return obj
         cmd = common + defs + ["-c", os.path.join(CSRC, src), "-o", obj]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:

@@ -106,6 +106,9 @@ def test_sketch_ragged_rows_vs_oracle(fo, n, G, d, density):
     (700, 1500, 9, 128, 0.6, 0.5, ""),         # rows longer than the 512-entry register prefetch
     (2, 70000, 5, 128, 0.01, 0.2, ""),         # gene axis too wide for the shared-memory tables -> v1 kernel
     (400, 2000, 12, 128, 0.1, 0.4, "FDB_SKETCH_V1"),
+    (1003, 18000, 30, 512, 0.02, 0.18, ""),    # the C3 shape (rows of ~360 entries, ~65 selected), n % 4 != 0
+    (37, 600, 50, 512, 0.9, 1.0, ""),          # wide rows (Kp = 56) + every row overflows the list
+    (5, 100, 3, 8, 0.5, 0.5, ""),              # fewer rows than one warp batch pair, tiny sketch
     (300, 3000, 7, 512, 0.3, 1.0, "FDB_SKETCH_V2"),
     (500, 2500, 40, 256, 0.1, 0.5, "FDB_SKETCH_V2"),
 ])
@@ -129,6 +132,48 @@ def test_fused_sketch_ragged_vs_oracle(fo, monkeypatch, n, G, K, d, density, fra
     assert rel(path.h.cpu().numpy()[:, :K], Ys @ tables.X_sketch.T) <= Y_REL_TOL
     assert rel(path.ysq.cpu().numpy(), (Ys ** 2).sum(1)) <= Y_REL_TOL
     assert np.all(path.h.cpu().numpy()[:, K:] == 0)
+
+
+def test_fused_sketch_mixed_batches_row_ids_and_linear(fo):
+    """v4 batches four rows per warp: rows that overflow the compaction list next to short and empty rows in the
+    same batch, a row subset in arbitrary order (row_ids, the multi-GPU tile form) and the linear (raw) transform."""
+    import torch
+    from flashdeconv_b200 import pipeline as pl
+    from flashdeconv_b200._native import check, lib
+    rng = np.random.default_rng(17)
+    n, G, K, d = 203, 4000, 11, 256
+    dens = rng.choice([0.0, 0.01, 0.05, 0.9], size=n, p=[0.1, 0.4, 0.3, 0.2])
+    rows = [sparse.random(1, G, density=float(q), format="csr", random_state=np.random.RandomState(i),
+                          data_rvs=lambda s: rng.integers(1, 40, s).astype(np.float64)) for i, q in enumerate(dens)]
+    Y = sparse.vstack(rows).tocsr()
+    X = rng.random((K, G)) + 0.05
+    gene_idx = np.sort(rng.choice(G, size=G // 2, replace=False))
+    lev = rng.random(gene_idx.size)
+    csr = pl.csr_to_device(Y)
+    for mode in ("log_cpm", "raw"):
+        tables = pl.build_tables(X, gene_idx, lev, d, 5, G, preprocess=mode)
+        path = pl.DevicePath(csr, torch.zeros((n, 2), dtype=torch.float64, device="cuda"), tables, K)
+        if mode == "log_cpm":
+            Ys = fo.sketch_full_csr(Y, gene_idx, tables.bucket, tables.weight, d)
+        else:
+            Ys = (Y[:, gene_idx] @ fo.omega_matrix(tables.bucket, tables.weight, d)).toarray()
+        want_h, want_sq = Ys @ tables.X_sketch.T, (Ys ** 2).sum(1)
+        path.stage_sketch()
+        torch.cuda.synchronize()
+        assert rel(path.h.cpu().numpy()[:, :K], want_h) <= Y_REL_TOL
+        assert rel(path.ysq.cpu().numpy(), want_sq) <= Y_REL_TOL
+        # a shuffled subset of rows through row_ids (outputs in subset order)
+        ids = rng.permutation(n)[:150].astype(np.int32)
+        ids_d = torch.from_numpy(ids).cuda()
+        h = torch.full((150, path.Kp), float("nan"), dtype=torch.float32, device="cuda")
+        sq = torch.full((150,), float("nan"), dtype=torch.float32, device="cuda")
+        fn = lib.fdb_sketch_linear_contract_csr if tables.linear else lib.fdb_sketch_contract_csr
+        check(fn(pl._ptr(csr.indptr), int(csr.indptr.dtype == torch.int64), pl._ptr(csr.indices), pl._ptr(csr.data), 150, G,
+                 pl._ptr(path.gene_bucket), pl._ptr(path.gene_weight), d, pl._ptr(path.x_sketch_t), K, pl._ptr(None),
+                 pl._ptr(ids_d), int(len(tables.bucket)), pl._ptr(h), pl._ptr(sq), pl._stream(torch)))
+        torch.cuda.synchronize()
+        assert rel(h.cpu().numpy()[:, :K], want_h[ids]) <= Y_REL_TOL
+        assert rel(sq.cpu().numpy(), want_sq[ids]) <= Y_REL_TOL
 
 
 def test_sweep_kernel_variants_agree():
