@@ -676,6 +676,7 @@ sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
                           float *__restrict__ h, float *__restrict__ ysq, int linear)
 {
     constexpr int XS = NK * 32;                                                         // floats per staged X_s^T row
+    constexpr int PF = NK == 1 ? 16 : 8;      // register-prefetched chunks of 32 entries (wide rows hold 64 accumulators)
     extern __shared__ unsigned char smem_raw[];
     __shared__ int scan_warp[32];
     __shared__ float s_wmax;
@@ -771,16 +772,29 @@ sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
     sk_u64 hv[NK * 16];                                                                 // NK x 8 chunk blocks (float pairs)
     // lane-parallel AXPY over list[0, n) with the row's scale
     auto flush = [&](int n, float scale) {
+        // software-pipelined: the record and (bucket, weight) of the next iteration are fetched before this
+        // iteration's eight row chunks, so the dependent LDS chain overlaps the FFMA2 block
+        float2 rec = make_float2(0.f, 0.f);
+        int2 bw = make_int2(0, 0);
+        if (lane < n) {
+            rec = list[lane];
+            bw = slot_bw[__float_as_int(rec.y)];
+        }
 #pragma unroll 1
         for (int t0 = 0; t0 < n; t0 += 32) {
-            const int t = t0 + lane;
-            if (t < n) {
-                const float2 rec = list[t];
-                const int2 bw = slot_bw[__float_as_int(rec.y)];
-                const float c = sk_xform(rec.x, scale) * __int_as_float(bw.y);
-                if (FIXED) atomicAdd(acc + bw.x, __float2int_rn(c * q_scale));
-                else atomicAdd(reinterpret_cast<float *>(acc) + bw.x, c);
-                const unsigned a0 = xs_lane + (unsigned)bw.x * (XS * 4);
+            const bool on = t0 + lane < n;
+            const float v = rec.x;
+            const int2 cur = bw;
+            const int tn = t0 + 32 + lane;
+            if (tn < n) {
+                rec = list[tn];
+                bw = slot_bw[__float_as_int(rec.y)];
+            }
+            if (on) {
+                const float c = sk_xform(v, scale) * __int_as_float(cur.y);
+                if (FIXED) atomicAdd(acc + cur.x, __float2int_rn(c * q_scale));
+                else atomicAdd(reinterpret_cast<float *>(acc) + cur.x, c);
+                const unsigned a0 = xs_lane + (unsigned)cur.x * (XS * 4);
                 const sk_u64 cc = sk_pack(c, c);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -814,8 +828,8 @@ sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
 
     // 32-bit offsets inside a row (rows longer than 2^31 entries are rejected on the host)
     int64_t it = (int64_t)blockIdx.x * warps_per_cta + warp;
-    int pg[kPrefetch];
-    float pv[kPrefetch];
+    int pg[PF];
+    float pv[PF];
     int64_t s = 0, row = 0;
     int len = 0;
     if (it < n_spots) {
@@ -827,7 +841,7 @@ sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
         const int32_t *ip = indices + s;
         const float *vp = counts + s;
 #pragma unroll
-        for (int u = 0; u < kPrefetch; ++u) {
+        for (int u = 0; u < PF; ++u) {
             const int j = 32 * u + lane;
             pg[u] = j < len ? ld_stream(ip + j) : pad_gene;
             pv[u] = j < len ? ld_stream(vp + j) : 0.f;
@@ -843,18 +857,18 @@ sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
             len2 = (int)(load_ptr(indptr, row2 + 1) - s2);
         }
 #pragma unroll
-        for (int i = 0; i < NK * 16; ++i) hv[i] = 0ull;
+        for (int i = 0; i < NK * 16; ++i) asm volatile("mov.b64 %0, 0;" : "=l"(hv[i]));
         int cnt = 0;
         float lib = 0.f;
 #pragma unroll
-        for (int u = 0; u < kPrefetch; ++u) {
+        for (int u = 0; u < PF; ++u) {
             if (32 * u >= len) break;                                     // warp-uniform
             take(pg[u], pv[u], cnt, lib);
         }
         {
             const int32_t *ip = indices + s;
             const float *vp = counts + s;
-            for (int j0 = 32 * kPrefetch; j0 < len; j0 += 128) {          // long rows: the rest, 4 chunks at a time
+            for (int j0 = 32 * PF; j0 < len; j0 += 128) {          // long rows: the rest, 4 chunks at a time
                 int g[4];
                 float v[4];
 #pragma unroll
@@ -879,7 +893,7 @@ sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
             const int32_t *ip = indices + s2;
             const float *vp = counts + s2;
 #pragma unroll
-            for (int u = 0; u < kPrefetch; ++u) {
+            for (int u = 0; u < PF; ++u) {
                 const int j = 32 * u + lane;
                 pg[u] = j < len2 ? ld_stream(ip + j) : pad_gene;
                 pv[u] = j < len2 ? ld_stream(vp + j) : 0.f;
