@@ -15,8 +15,6 @@
 //   this file                   bcd_sweep_kernel: fp32-gather sweep, one patch per CTA -- the fallback when the spatial
 //                               coupling is strong (fp16 neighbour values inadmissible) or no gather plan is given;
 //                               bcd_plan_kernel: per-patch halo lists and neighbour codes, built once per graph;
-//                               bcd_sweep_h_kernel / bcd_sweep_d_kernel: comparison kernels (FDB_SWEEP_VARIANT=4 / 6,
-//                               Kp = 32 only: one patch per CTA; persistent with two spots per lane);
 //                               dispatcher, objective terms (float64 accumulation), proportions, C entry points.
 //   Common to all sweep kernels: thread per spot for the strictly sequential K-step coordinate descent, evaluated in
 //   the direct form part_k = c_k - sum_{j!=k} G_kj b_j (K^2 FMAs per spot, the dense minimum; the reference's
@@ -204,20 +202,13 @@ bcd_sweep_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP
 }
 
 // ------------------------------------------------------------------------------------
-// Sweep kernel, halo-staged form with a half-precision gather tile, one patch per CTA (comparison kernel,
-// FDB_SWEEP_VARIANT=4, Kp = 32; the production kernel in bcd_p.cuh keeps its gather tile and adds the pipeline).
-//
-// Same four steps as bcd_sweep_kernel, with the neighbour gather made a pure shared-memory operation:
-//   * the CTA's TILE beta_old rows are staged twice: fp32 (own rows, needed exactly by the descent) and as an
-//     fp16 GATHER tile (64-byte rows for Kp = 32);
-//   * neighbours outside the patch are given a slot in a halo extension of the gather tile (smem atomic
-//     counter), and their rows are then fetched ONCE per CTA with coalesced loads -- instead of every lane
-//     chasing its own 128-byte row through L2 in every round (40 L1 wavefronts per round before);
-//   * the gather reads only fp16 rows from shared memory (4 LDS.128 per neighbour) and accumulates in half2.
-// Why fp16 is admissible for the neighbour sum only: it enters the update as lam*sum with
-// lam*deg ~ 0.5 % of G_kk (core/spatial.py:181-190), so a 5e-4 relative rounding of a neighbour value moves
-// beta by ~1e-7 relative, three orders below the 1e-4 parity bar; the spot's own row, H and the Gram
-// products stay fp32.  (tests/test_gpu_parity.py holds both variants to the same bars.)
+// Gather plan for the production sweep kernel (bcd_p.cuh): the CTA's TILE beta_old rows are staged twice -- fp32 (own
+// rows, needed exactly by the descent) and as an fp16 GATHER tile; neighbours outside the patch get a slot in a halo
+// extension of the gather tile and are fetched ONCE per CTA with coalesced loads, so the gather itself is a pure
+// shared-memory operation.  Why fp16 is admissible for the neighbour sum only: it enters the update as lam*sum with
+// lam*deg ~ 0.5 % of G_kk (core/spatial.py:181-190), so a 5e-4 relative rounding of a neighbour value moves beta by
+// ~1e-7 relative, three orders below the 1e-4 parity bar; the spot's own row, H and the Gram products stay fp32, and
+// the tile is range-scaled per sweep (bcd_p.cuh) so magnitude never matters.
 // ------------------------------------------------------------------------------------
 template <int TILE>
 __global__ void __launch_bounds__(TILE)
@@ -284,558 +275,6 @@ bcd_plan_kernel(const int32_t *__restrict__ indptr, const int32_t *__restrict__ 
     if ((int)threadIdx.x >= min(count, kHaloSlots)) halo_rows[(int64_t)blockIdx.x * HCAP + threadIdx.x] = -1;
 }
 
-template <int KP, int NW, int MINB>
-__global__ void __launch_bounds__(NW * 32, MINB)
-bcd_sweep_h_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP> G,
-                   const float *__restrict__ beta_in, float *__restrict__ beta_out,
-                   const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, PlanView plan,
-                   int n_rows, int n_types, float lam, float rho, float tol, int finalize, SolveState *state,
-                   int pf_stride)
-{
-    static_assert(KP % 8 == 0, "half gather rows need Kp % 8 == 0");
-    const int already_converged = *reinterpret_cast<volatile int *>(&state->converged);
-
-    using L = TileLayout<KP>;
-    constexpr int Q = L::Q, S = L::S, TILE = NW * 32, HCAP = TILE;
-    constexpr int GQ = Q / 2;                            // 16-byte chunks per fp16 gather row
-    constexpr int GROW = KP / 2;                         // 32-bit words per gather row
-    extern __shared__ __align__(16) float sweep_smem[];
-    float *c_tile = sweep_smem;                                                   // TILE x S fp32
-    uint32_t *g_tile = reinterpret_cast<uint32_t *>(sweep_smem + TILE * S);       // (TILE + HCAP) x GROW words
-    uint16_t *idx_tile = reinterpret_cast<uint16_t *>(g_tile + (TILE + HCAP) * GROW);   // NW x kIdxCap codes
-    __shared__ unsigned red[2][NW];
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int tile_base = blockIdx.x * TILE;
-    const int wrow = warp * 32;
-    uint16_t *iw = idx_tile + warp * kIdxCap;
-
-    // ---------------- step 0: everything this patch reads from global is requested up front:
-    //   row pointers, the warp's beta_old rows (-> fp32 tile + fp16 gather tile), the patch's foreign halo
-    //   rows (-> fp16 gather tile extension) and the warp's slice of neighbour codes
-    const int my_row = tile_base + wrow + lane;
-    int my_s = 0, my_e = 0;
-    if (my_row < n_rows) { my_s = __ldg(indptr + my_row); my_e = __ldg(indptr + my_row + 1); }
-    const int halo_id = __ldg(plan.halo_rows + (size_t)blockIdx.x * HCAP + threadIdx.x);   // slot = thread, -1 = unused
-    auto to_gather = [&](int grow, int q, const float4 bb) {
-        const __half2 lo = __floats2half2_rn(bb.x, bb.y), hi = __floats2half2_rn(bb.z, bb.w);
-        uint2 pk;
-        pk.x = *reinterpret_cast<const uint32_t *>(&lo);
-        pk.y = *reinterpret_cast<const uint32_t *>(&hi);
-        *reinterpret_cast<uint2 *>(g_tile + grow * GROW + 4 * ((q >> 1) ^ gsw<GQ>(grow)) + 2 * (q & 1)) = pk;
-    };
-#pragma unroll
-    for (int i = 0; i < Q; ++i) {
-        const int idx = lane + 32 * i;
-        const int lr = idx / Q, q = idx - lr * Q;
-        const int p = tile_base + wrow + lr;
-        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p < n_rows) bb = ld4(beta_in + (size_t)p * KP + 4 * q);
-        st4(c_tile + L::at(wrow + lr, q), bb);
-        to_gather(wrow + lr, q, bb);
-    }
-    // halo rows of this warp's 32 slots: the row ids travel by shuffle, so the row loads depend on one earlier
-    // load only (no shared-memory hand-off, no extra barrier)
-#pragma unroll
-    for (int i = 0; i < Q; ++i) {
-        const int idx = lane + 32 * i;
-        const int lr = idx / Q, q = idx - lr * Q;
-        const int g = __shfl_sync(kFull, halo_id, lr);
-        if (g >= 0) to_gather(TILE + wrow + lr, q, ld4(beta_in + (size_t)g * KP + 4 * q));
-    }
-    const int my_deg = my_e - my_s;
-    const int ibase = __shfl_sync(kFull, my_s, 0);
-    const int icnt = __reduce_max_sync(kFull, my_e - ibase);
-    const bool staged = icnt <= kIdxCap;
-    if (staged)
-        for (int t = lane; t < icnt; t += 32) iw[t] = plan.codes[ibase + t];
-    // pull the rows of the patch that runs on this SM slot one wave from now into L2 (one 128-byte line of
-    // beta_old and one of H per thread), so its start-of-CTA loads are L2 hits instead of DRAM round trips
-    if (pf_stride > 0) {
-        const int64_t prow = (int64_t)(blockIdx.x + pf_stride) * TILE + threadIdx.x;
-        if (prow < n_rows) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(beta_in + prow * KP));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(h + prow * KP));
-        }
-    }
-    __syncthreads();                                     // tiles, halo rows and code slices are in shared memory
-    if (already_converged) return;                       // uniform across the grid
-
-    // ---------------- step 1: own beta_old row -> registers (fp32), thread per spot
-    const int rs = my_s - ibase;
-    float2 b2[KP / 2];
-#pragma unroll
-    for (int q = 0; q < Q; ++q) {
-        const float4 b4 = ld4(c_tile + L::at(wrow + lane, q));
-        b2[2 * q] = make_float2(b4.x, b4.y);
-        b2[2 * q + 1] = make_float2(b4.z, b4.w);
-    }
-    __syncwarp();
-    // the warp's fp32 rows are free again: H rows stream into them asynchronously (LDGSTS, no registers)
-    // while the neighbour sums are formed
-#pragma unroll
-    for (int i = 0; i < Q; ++i) {
-        const int idx = lane + 32 * i;
-        const int lr = idx / Q, q = idx - lr * Q;
-        const int p = tile_base + wrow + lr;
-        if (p < n_rows) {
-            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(c_tile + L::at(wrow + lr, q));
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(h + (size_t)p * KP + 4 * q));
-        } else {
-            st4(c_tile + L::at(wrow + lr, q), make_float4(0.f, 0.f, 0.f, 0.f));
-        }
-    }
-    asm volatile("cp.async.commit_group;");
-
-    // ---------------- step 2: neighbour sums from the fp16 gather tile, one spot per lane
-    __half2 acc[KP / 2];
-    {
-#pragma unroll
-        for (int i = 0; i < KP / 2; ++i) acc[i] = __floats2half2_rn(0.f, 0.f);
-        const int own = wrow + lane;
-        const int maxdeg = __reduce_max_sync(kFull, my_deg);
-#pragma unroll 1
-        for (int u = 0; u < maxdeg; ++u) {
-            const bool has = u < my_deg;
-            unsigned code = own;
-            if (has) code = staged ? iw[rs + u] : plan.codes[my_s + u];
-            if (__any_sync(kFull, code == kCodeSlow)) {  // rare: more foreign rows than halo slots -> fp32 row from global
-                if (code == kCodeSlow) {
-                    const float *src = beta_in + (size_t)__ldg(indices + my_s + u) * KP;
-#pragma unroll
-                    for (int q = 0; q < Q; ++q) {
-                        const float4 v = ld4(src + 4 * q);
-                        acc[2 * q] = __hadd2(acc[2 * q], __floats2half2_rn(v.x, v.y));
-                        acc[2 * q + 1] = __hadd2(acc[2 * q + 1], __floats2half2_rn(v.z, v.w));
-                    }
-                }
-            }
-            // lanes without a (shared-memory) neighbour this round re-read their own row with weight 0
-            const bool use = has && code != kCodeSlow;
-            const __half2 m = use ? __floats2half2_rn(1.f, 1.f) : __floats2half2_rn(0.f, 0.f);
-            const int grow = use ? (int)code : own;
-            const uint4 *row = reinterpret_cast<const uint4 *>(g_tile + grow * GROW);
-            const int sw = gsw<GQ>(grow);
-#pragma unroll
-            for (int q = 0; q < GQ; ++q) {
-                const uint4 w = row[q ^ sw];
-                acc[4 * q] = __hfma2(*reinterpret_cast<const __half2 *>(&w.x), m, acc[4 * q]);
-                acc[4 * q + 1] = __hfma2(*reinterpret_cast<const __half2 *>(&w.y), m, acc[4 * q + 1]);
-                acc[4 * q + 2] = __hfma2(*reinterpret_cast<const __half2 *>(&w.z), m, acc[4 * q + 2]);
-                acc[4 * q + 3] = __hfma2(*reinterpret_cast<const __half2 *>(&w.w), m, acc[4 * q + 3]);
-            }
-        }
-    }
-    asm volatile("cp.async.wait_all;");
-    __syncwarp();                                        // the warp's H rows have landed in its fp32 tile rows
-
-    // ---------------- step 3: cyclic coordinate descent, direct form on packed FFMA2
-    //   part_k = c_k - rho - sum_{j != k} G_kj b_j  (b_j already updated for j < k),  b_k <- max(0, part_k / den_k)
-    // beta lives in 64-bit register pairs, so every FFMA2 takes its beta operand as is.  The two accumulation
-    // chains of step k walk the pairs from the least to the most recently updated one (a rotation starting
-    // right behind beta_k), so only the last link of each chain waits for step k-1: the serial path per step is
-    // FFMA2 -> ADD2 -> FADD -> FMUL -> FMNMX and the other Kp/2-2 FFMA2 of the step fill those latency slots.
-    // (The select on the reciprocal also keeps cicc's compile time sane: without it NVVM spends > 10 min on Kp = 64.)
-    float dmax = 0.f, amax = 0.f;
-    {
-        constexpr int NP = KP / 2;
-        const int trow = wrow + lane;
-        const float lam_deg = lam * (float)my_deg;
-        const float neg_rho = -rho;
-        u64 bq[NP];
-#pragma unroll
-        for (int p = 0; p < NP; ++p) {
-            amax = fmaxf(amax, fmaxf(fabsf(b2[p].x), fabsf(b2[p].y)));
-            bq[p] = pack2(b2[p].x, b2[p].y);
-        }
-        static_for<0, Q>([&](auto qc) {
-            constexpr int q = decltype(qc)::value;
-            const float4 c4 = ld4(c_tile + L::at(trow, q));
-            const float2 s01 = __half22float2(acc[2 * q]), s23 = __half22float2(acc[2 * q + 1]);
-            const float4 ns4 = make_float4(s01.x, s01.y, s23.x, s23.y);
-            float4 n4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            static_for<0, 4>([&](auto jc) {
-                constexpr int j = decltype(jc)::value;
-                constexpr int k = 4 * q + j;
-                if (k >= KP - 7 && k >= n_types) return;            // padding columns stay zero (warp-uniform)
-                const float den = G.diag[k] + lam_deg;
-                const float rinv = den > 1e-10f ? rcp_fast(den) : 0.f;   // core/solver.py:87-90: denominator <= 1e-10 -> 0
-                u64 a0 = pack2(fmaf(lam, elem(ns4, j), elem(c4, j)), neg_rho), a1 = 0ull;
-                constexpr int start = (k + 1) >> 1;
-                static_for<0, NP>([&](auto ic) {
-                    constexpr int i = decltype(ic)::value;
-                    constexpr int jj = (start + i) % NP;
-                    const u64 g = pack2(G.g[k * KP + 2 * jj], G.g[k * KP + 2 * jj + 1]);
-                    if constexpr (i & 1) ffma2q(a1, g, bq[jj]); else ffma2q(a0, g, bq[jj]);
-                });
-                float lo, hi, s0, s1;
-                unpack2(add2q(a0, a1), s0, s1);
-                const float nv = fmaxf(0.f, (s0 + s1) * rinv);
-                unpack2(bq[k >> 1], lo, hi);
-                if constexpr (k & 1) {
-                    dmax = fmaxf(dmax, fabsf(nv - hi));
-                    bq[k >> 1] = pack2(lo, nv);
-                } else {
-                    dmax = fmaxf(dmax, fabsf(nv - lo));
-                    bq[k >> 1] = pack2(nv, hi);
-                }
-                set_elem(n4, j, nv);
-            });
-            st4(c_tile + L::at(trow, q), n4);
-        });
-        if (my_row >= n_rows) { dmax = 0.f; amax = 0.f; }
-    }
-    __syncwarp();
-
-    // ---------------- step 4: stream the warp's new rows out
-#pragma unroll
-    for (int i = 0; i < Q; ++i) {
-        const int idx = lane + 32 * i;
-        const int lr = idx / Q, q = idx - lr * Q;
-        const int p = tile_base + wrow + lr;
-        if (p < n_rows) st4(beta_out + (size_t)p * KP + 4 * q, ld4(c_tile + L::at(wrow + lr, q)));
-    }
-
-    const unsigned wd = __reduce_max_sync(kFull, __float_as_uint(dmax));
-    const unsigned wa = __reduce_max_sync(kFull, __float_as_uint(amax));
-    if (lane == 0) { red[0][warp] = wd; red[1][warp] = wa; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned bd = 0u, ba = 0u;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) { bd = max(bd, red[0][w]); ba = max(ba, red[1][w]); }
-        if (bd > *reinterpret_cast<volatile unsigned *>(&state->max_diff_bits)) atomicMax(&state->max_diff_bits, bd);
-        if (ba > *reinterpret_cast<volatile unsigned *>(&state->max_abs_bits)) atomicMax(&state->max_abs_bits, ba);
-        if (finalize) {
-            __threadfence();
-            if (atomicAdd(&state->arrived, 1u) == gridDim.x - 1) {
-                __threadfence();
-                finalize_state(state, tol);
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------
-// Sweep kernel, persistent pipelined form with TWO spots per lane (comparison kernel, FDB_SWEEP_VARIANT=6, Kp = 32:
-// 18 % fewer instructions than the production kernel but 12 warps/SM; measured 122 vs 99 us per sweep at C3).
-//
-// Same pipeline as bcd_sweep_p_kernel (scalars, codes and rows of patch p+1 requested while p is computed), but
-// a CTA is 2 warps = 64 lanes for a 128-spot patch and lane l of warp w owns spots a = 64 w + l and b = a + 32.
-// The coordinate descent keeps beta as pairs ACROSS the two spots, bp[j] = (beta_a[j], beta_b[j]), so that
-//   * one FFMA2 is one column j for both spots and its Gram operand is a single broadcast uniform register
-//     (FFMA2 R, R.F32x2, UR.F32): one LDCU.128 feeds four FFMA2 -- half the constant loads per spot;
-//   * the accumulator halves ARE the two spots' partial sums: no horizontal reduction, and the updated pair
-//     (new_a, new_b) replaces bp[k] as a whole: no re-packing moves;
-//   * the rest of the step (threshold, reciprocal scale, max-norm statistics) runs on packed f32x2 too.
-// 64-thread CTAs at 6 per SM leave 168 registers per thread, so nothing spills.
-// ------------------------------------------------------------------------------------
-// PADC: trailing all-padding columns (Kp - K >= PADC) left out of the descent at compile time
-template <int KP, int MINB, int PADC>
-__global__ void __launch_bounds__(64, MINB)
-bcd_sweep_d_kernel(const float *__restrict__ h, const __grid_constant__ GramArg<KP> G,
-                   const float *__restrict__ beta_in, float *__restrict__ beta_out,
-                   const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, PlanView plan,
-                   int n_rows, int n_types, float lam, float rho, float tol, int finalize, SolveState *state,
-                   int n_patches)
-{
-    static_assert(KP % 8 == 0, "half gather rows need Kp % 8 == 0");
-    using L = TileLayout<KP>;
-    constexpr int Q = L::Q, S = L::S, TILE = 128, HCAP = TILE, NT = 64;
-    constexpr int GQ = Q / 2;                            // 16-byte chunks per fp16 gather row
-    constexpr int GROW = KP / 2;                         // 32-bit words per gather row
-    extern __shared__ __align__(16) float sweep_smem[];
-    float *c_tile = sweep_smem;                                                   // TILE x S fp32: beta_old, H, beta_new
-    uint32_t *g_tile = reinterpret_cast<uint32_t *>(c_tile + TILE * S);           // (TILE + HCAP) x GROW words
-    uint8_t *idx_tile = reinterpret_cast<uint8_t *>(g_tile + (TILE + HCAP) * GROW);     // 4 groups x kCodeRounds x 32 codes
-    int *scal = reinterpret_cast<int *>(idx_tile + 4 * kCodeRounds * 32);         // 3 x TILE: row start, end, halo id
-    __shared__ unsigned red[2][2];
-
-    if (*reinterpret_cast<volatile int *>(&state->converged)) return;      // uniform across the grid
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wrow = warp * 64;                          // the warp's 64 rows of the patch
-    const int own_a = wrow + lane, own_b = own_a + 32;
-    uint8_t *iw_a = idx_tile + (2 * warp) * (kCodeRounds * 32) + lane;
-    uint8_t *iw_b = iw_a + kCodeRounds * 32;
-
-    // asynchronous copy of the warp's 64 rows of `src` (patch `pp`) into c_tile
-    auto rows_async = [&](const float *__restrict__ src, int pp) {
-#pragma unroll
-        for (int i = 0; i < 2 * Q; ++i) {
-            const int idx = lane + 32 * i;
-            const int lr = idx / Q, q = idx - lr * Q;
-            const int p = pp * TILE + wrow + lr;
-            const uint32_t d = (uint32_t)__cvta_generic_to_shared(c_tile + L::at(wrow + lr, q));
-            const int nbytes = p < n_rows ? 16 : 0;                               // rows past the end: zero fill
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d),
-                         "l"(src + (size_t)min(p, n_rows - 1) * KP + 4 * q), "r"(nbytes));
-        }
-    };
-    // row pointers of the lane's two spots and halo ids of its two halo slots (32 w + lane, 64 + 32 w + lane) of
-    // patch `pp` -> this thread's private words of scal
-    auto scalars_async = [&](int pp) {
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int lrow = own_a + 32 * half;
-            const int r = pp * TILE + lrow;
-            const int nb = r < n_rows ? 4 : 0;
-            const int32_t *src = indptr + min(r, n_rows - 1);
-            const uint32_t d = (uint32_t)__cvta_generic_to_shared(scal + lrow);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(nb));
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d + 4 * TILE), "l"(src + 1), "r"(nb));
-            const int slot = 64 * half + 32 * warp + lane;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::
-                         "r"((uint32_t)__cvta_generic_to_shared(scal + 2 * TILE + slot)),
-                         "l"(plan.halo_rows + (size_t)pp * HCAP + slot));
-        }
-    };
-
-    // everything patch `pp` needs at its start (its scalars are in scal): the warp's 64 beta_old rows and its 64
-    // halo rows into registers (coalesced; halo ids travel by shuffle), its two code blocks into idx_tile
-    auto load_patch = [&](int pp, float4 (&hrow)[2 * Q]) {
-        const int d_a = scal[TILE + own_a] - scal[own_a], d_b = scal[TILE + own_b] - scal[own_b];
-        const int m_a = __reduce_max_sync(kFull, d_a), m_b = __reduce_max_sync(kFull, d_b);
-        if (max(m_a, m_b) <= kCodeRounds) {              // transposed byte codes of the two 32-row groups
-            const uint8_t *src = plan.codes8 + ((size_t)pp * 4 + 2 * warp) * (kCodeRounds * 32) + 16 * lane;
-            if (lane < 2 * m_a)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::
-                             "r"((uint32_t)__cvta_generic_to_shared(iw_a + 15 * lane)), "l"(src));
-            if (lane < 2 * m_b)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::
-                             "r"((uint32_t)__cvta_generic_to_shared(iw_b + 15 * lane)), "l"(src + kCodeRounds * 32));
-        }
-        asm volatile("cp.async.commit_group;");
-        rows_async(beta_in, pp);
-        asm volatile("cp.async.commit_group;");
-        const int hid0 = scal[2 * TILE + 32 * warp + lane], hid1 = scal[2 * TILE + 64 + 32 * warp + lane];
-#pragma unroll
-        for (int i = 0; i < 2 * Q; ++i) {
-            const int idx = lane + 32 * i;
-            const int lr = idx / Q, q = idx - lr * Q;
-            const int g = __shfl_sync(kFull, lr < 32 ? hid0 : hid1, lr & 31);
-            hrow[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (g >= 0) hrow[i] = ld4(beta_in + (size_t)g * KP + 4 * q);
-        }
-    };
-
-    int patch = blockIdx.x;
-    scalars_async(patch);
-    asm volatile("cp.async.commit_group;");
-    asm volatile("cp.async.wait_all;");
-
-    float dmax = 0.f, amax = 0.f;
-#pragma unroll 1
-    for (; patch < n_patches; patch += gridDim.x) {
-        const int tile_base = patch * TILE;
-        const int next = patch + gridDim.x;
-        const int sa = scal[own_a], ea = scal[TILE + own_a], sb = scal[own_b], eb = scal[TILE + own_b];
-        const int deg_a = ea - sa, deg_b = eb - sb;
-        const int md_a = __reduce_max_sync(kFull, deg_a), md_b = __reduce_max_sync(kFull, deg_b);
-        const bool staged = max(md_a, md_b) <= kCodeRounds;
-        float4 hrow[2 * Q];
-        load_patch(patch, hrow);
-        asm volatile("cp.async.wait_all;");              // the warp's beta_old rows and code blocks
-        __syncthreads();                 // (1) both warps are past the gather of the previous patch: g_tile is free
-        auto to_gather = [&](int grow, int q, const float4 bb) {
-            const __half2 lo = __floats2half2_rn(bb.x, bb.y), hi = __floats2half2_rn(bb.z, bb.w);
-            uint2 pk;
-            pk.x = *reinterpret_cast<const uint32_t *>(&lo);
-            pk.y = *reinterpret_cast<const uint32_t *>(&hi);
-            *reinterpret_cast<uint2 *>(g_tile + grow * GROW + 4 * ((q >> 1) ^ gsw<GQ>(grow)) + 2 * (q & 1)) = pk;
-        };
-#pragma unroll
-        for (int i = 0; i < 2 * Q; ++i) {
-            const int idx = lane + 32 * i;
-            const int lr = idx / Q, q = idx - lr * Q;
-            const int slot = lr < 32 ? 32 * warp + lr : 64 + 32 * warp + (lr - 32);
-            to_gather(TILE + slot, q, hrow[i]);
-            to_gather(wrow + lr, q, ld4(c_tile + L::at(wrow + lr, q)));
-        }
-        // own beta_old rows -> registers, paired across the two spots
-        u64 bp[KP];
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-            const float4 a4 = ld4(c_tile + L::at(own_a, q)), b4 = ld4(c_tile + L::at(own_b, q));
-            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(a4.x), fabsf(a4.y)), fmaxf(fabsf(a4.z), fabsf(a4.w))));
-            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(b4.x), fabsf(b4.y)), fmaxf(fabsf(b4.z), fabsf(b4.w))));
-            // through an f32x2 add: ptxas re-materialises a bare mov.b64 {a, b} in front of every FFMA2 that reads
-            // it (two MOVs per use), while the result of an arithmetic instruction stays in its aligned pair
-            bp[4 * q] = add2q(packm(a4.x, b4.x), 0ull);
-            bp[4 * q + 1] = add2q(packm(a4.y, b4.y), 0ull);
-            bp[4 * q + 2] = add2q(packm(a4.z, b4.z), 0ull);
-            bp[4 * q + 3] = add2q(packm(a4.w, b4.w), 0ull);
-        }
-        __syncthreads();                 // (2) gather tile complete; the fp32 rows are consumed
-
-        // ---------------- requests: H rows of this patch -> c_tile; the next patch's scalars -> scal, rows -> L2
-        rows_async(h, patch);
-        if (next < n_patches) {
-            scalars_async(next);
-            const size_t base = (size_t)next * TILE * KP;
-            const int lines = min(TILE, n_rows - next * TILE) * KP / 32;       // 128-byte lines of the patch's rows
-            for (int l = tid; l < lines; l += NT) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(beta_in + base + (size_t)l * 32));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(h + base + (size_t)l * 32));
-            }
-        }
-        asm volatile("cp.async.commit_group;");
-
-        // ---------------- neighbour sums from the fp16 gather tile: round u adds, for both spots of the lane, the
-        // gather-tile row named by the u-th byte code (the all-zero row 254 past the end of a list)
-        __half2 acc_a[KP / 2], acc_b[KP / 2];
-        {
-#pragma unroll
-            for (int i = 0; i < KP / 2; ++i) { acc_a[i] = __floats2half2_rn(0.f, 0.f); acc_b[i] = acc_a[i]; }
-            auto add_row = [&](__half2 (&acc)[KP / 2], int grow) {
-                const uint4 *row = reinterpret_cast<const uint4 *>(g_tile + grow * GROW);
-                const int sw = gsw<GQ>(grow);
-#pragma unroll
-                for (int q = 0; q < GQ; ++q) {
-                    const uint4 w = row[q ^ sw];
-                    acc[4 * q] = __hadd2(*reinterpret_cast<const __half2 *>(&w.x), acc[4 * q]);
-                    acc[4 * q + 1] = __hadd2(*reinterpret_cast<const __half2 *>(&w.y), acc[4 * q + 1]);
-                    acc[4 * q + 2] = __hadd2(*reinterpret_cast<const __half2 *>(&w.z), acc[4 * q + 2]);
-                    acc[4 * q + 3] = __hadd2(*reinterpret_cast<const __half2 *>(&w.w), acc[4 * q + 3]);
-                }
-            };
-            auto add_slow = [&](__half2 (&acc)[KP / 2], int pos) {     // foreign row without a halo slot: fp32 row from global
-                const float *src = beta_in + (size_t)__ldg(indices + pos) * KP;
-#pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    const float4 v = ld4(src + 4 * q);
-                    acc[2 * q] = __hadd2(acc[2 * q], __floats2half2_rn(v.x, v.y));
-                    acc[2 * q + 1] = __hadd2(acc[2 * q + 1], __floats2half2_rn(v.z, v.w));
-                }
-            };
-            const int rounds = max(md_a, md_b);
-            if (staged) {
-                int na = md_a > 0 ? (int)iw_a[0] : kCodeZero8, nb = md_b > 0 ? (int)iw_b[0] : kCodeZero8;
-#pragma unroll 2
-                for (int u = 0; u < rounds; ++u) {
-                    int ca = na, cb = nb;                                   // codes are fetched one round ahead
-                    na = u + 1 < md_a ? (int)iw_a[(u + 1) * 32] : kCodeZero8;
-                    nb = u + 1 < md_b ? (int)iw_b[(u + 1) * 32] : kCodeZero8;
-                    if (__any_sync(kFull, ca == kCodeSlow8 || cb == kCodeSlow8)) {      // rare
-                        if (ca == kCodeSlow8) { add_slow(acc_a, sa + u); ca = kCodeZero8; }
-                        if (cb == kCodeSlow8) { add_slow(acc_b, sb + u); cb = kCodeZero8; }
-                    }
-                    add_row(acc_a, ca);
-                    add_row(acc_b, cb);
-                }
-            } else {                                     // a row with more than kCodeRounds neighbours: CSR-order codes
-#pragma unroll 1
-                for (int u = 0; u < rounds; ++u) {
-                    unsigned ca = kCodeZero8, cb = kCodeZero8;
-                    if (u < deg_a) ca = plan.codes[sa + u];
-                    if (u < deg_b) cb = plan.codes[sb + u];
-                    if (ca == kCodeSlow) { add_slow(acc_a, sa + u); ca = kCodeZero8; }
-                    if (cb == kCodeSlow) { add_slow(acc_b, sb + u); cb = kCodeZero8; }
-                    add_row(acc_a, (int)ca);
-                    add_row(acc_b, (int)cb);
-                }
-            }
-        }
-        asm volatile("cp.async.wait_all;");              // H rows of this patch, scalars of the next
-        __syncwarp();
-        if (next < n_patches) {                          // the next patch's halo rows and code blocks -> L2
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int nx_halo = scal[2 * TILE + 64 * half + 32 * warp + lane];
-                if (nx_halo >= 0) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(beta_in + (size_t)nx_halo * KP));
-                    if (KP > 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(beta_in + (size_t)nx_halo * KP + 32));
-                }
-            }
-            if (tid < 16)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(plan.codes8 + (size_t)next * 4 * (kCodeRounds * 32) + 128 * tid));
-        }
-
-        // ---------------- cyclic coordinate descent for both spots, direct form:
-        //   part_k = c_k - rho - sum_{j != k} G_kj b_j  (b_j already updated for j < k),  b_k <- max(0, part_k / den_k)
-        // Two accumulation chains per step walk the columns from the least to the most recently updated one
-        // (j = k+1, ..., Kp-1, 0, ..., k-1), so only the last link of each chain waits for step k-1.
-        {
-            const float ld_a = lam * (float)deg_a, ld_b = lam * (float)deg_b;
-            const u64 nrho2 = packm(-rho, -rho);
-            const u64 lam2 = packm(lam, lam);
-            u64 dm2 = 0ull;
-            static_for<0, Q>([&](auto qc) {
-                constexpr int q = decltype(qc)::value;
-                const float4 ca4 = ld4(c_tile + L::at(own_a, q)), cb4 = ld4(c_tile + L::at(own_b, q));
-                const float2 sa01 = __half22float2(acc_a[2 * q]), sa23 = __half22float2(acc_a[2 * q + 1]);
-                const float2 sb01 = __half22float2(acc_b[2 * q]), sb23 = __half22float2(acc_b[2 * q + 1]);
-                const float4 nsa = make_float4(sa01.x, sa01.y, sa23.x, sa23.y), nsb = make_float4(sb01.x, sb01.y, sb23.x, sb23.y);
-                float4 na4 = make_float4(0.f, 0.f, 0.f, 0.f), nb4 = na4;
-                static_for<0, 4>([&](auto jc) {
-                    constexpr int j = decltype(jc)::value;
-                    constexpr int k = 4 * q + j;
-                    if constexpr (k >= KP - PADC) return;               // padding columns stay zero
-                    if (k >= KP - 7 && k >= n_types) return;            // (warp-uniform)
-                    const float den_a = G.diag[k] + ld_a, den_b = G.diag[k] + ld_b;
-                    const float ri_a = den_a > 1e-10f ? rcp_fast(den_a) : 0.f;      // core/solver.py:87-90
-                    const float ri_b = den_b > 1e-10f ? rcp_fast(den_b) : 0.f;
-                    u64 a0 = fma2(packm(elem(nsa, j), elem(nsb, j)), lam2, packm(elem(ca4, j), elem(cb4, j)));
-                    u64 a1 = nrho2;
-                    static_for<1, KP>([&](auto ic) {
-                        constexpr int i = decltype(ic)::value;
-                        constexpr int jj = (k + i) % KP;
-                        if constexpr (jj < KP - PADC) {
-                            const float g = G.g[k * KP + jj];
-                            if constexpr (i & 1) a1 = fma2(pack2(g, g), bp[jj], a1); else a0 = fma2(pack2(g, g), bp[jj], a0);
-                        }
-                    });
-                    const u64 t2 = mul2q(add2q(a0, a1), packm(ri_a, ri_b));
-                    float ta, tb;
-                    unpackm(t2, ta, tb);
-                    const u64 nv2 = packm(fmaxf(0.f, ta), fmaxf(0.f, tb));
-                    const u64 d2 = sub2q(nv2, bp[k]);
-                    float da, db;
-                    unpackm(d2, da, db);
-                    float m0, m1;
-                    unpackm(dm2, m0, m1);
-                    dm2 = packm(fmaxf(m0, fabsf(da)), fmaxf(m1, fabsf(db)));
-                    bp[k] = nv2;
-                    set_elem(na4, j, fmaxf(0.f, ta));
-                    set_elem(nb4, j, fmaxf(0.f, tb));
-                });
-                st4(c_tile + L::at(own_a, q), na4);
-                st4(c_tile + L::at(own_b, q), nb4);
-            });
-            float m0, m1;
-            unpackm(dm2, m0, m1);
-            if (tile_base + own_a < n_rows) dmax = fmaxf(dmax, m0);
-            if (tile_base + own_b < n_rows) dmax = fmaxf(dmax, m1);
-        }
-        __syncwarp();
-
-#pragma unroll
-        for (int i = 0; i < 2 * Q; ++i) {
-            const int idx = lane + 32 * i;
-            const int lr = idx / Q, q = idx - lr * Q;
-            const int p = tile_base + wrow + lr;
-            if (p < n_rows) st4(beta_out + (size_t)p * KP + 4 * q, ld4(c_tile + L::at(wrow + lr, q)));
-        }
-    }
-
-    const unsigned wd = __reduce_max_sync(kFull, __float_as_uint(dmax));
-    const unsigned wa = __reduce_max_sync(kFull, __float_as_uint(amax));
-    if (lane == 0) { red[0][warp] = wd; red[1][warp] = wa; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned bd = max(red[0][0], red[0][1]), ba = max(red[1][0], red[1][1]);
-        if (bd > *reinterpret_cast<volatile unsigned *>(&state->max_diff_bits)) atomicMax(&state->max_diff_bits, bd);
-        if (ba > *reinterpret_cast<volatile unsigned *>(&state->max_abs_bits)) atomicMax(&state->max_abs_bits, ba);
-        if (finalize) {
-            __threadfence();
-            if (atomicAdd(&state->arrived, 1u) == gridDim.x - 1) {
-                __threadfence();
-                finalize_state(state, tol);
-            }
-        }
-    }
-}
-
 __global__ void bcd_finalize_kernel(SolveState *state, float tol)
 {
     if (state->converged) return;
@@ -848,6 +287,7 @@ bcd_init_kernel(float *__restrict__ beta, int64_t n_rows, int kp, int n_types, S
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && state) {
         SolveState z = {};
+        z.last_max_abs = n_types > 0 ? 1.0f / (float)n_types : 0.f;      // bound on |beta| for the first sweep (fp16 tile scale)
         *state = z;
     }
     if (i >= n_rows * kp) return;
@@ -872,7 +312,7 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
     for (int k = 0; k < KP; ++k) G.diag[k] = k < n_types ? host_gram[k * n_types + k] : 0.f;
     for (int k = 0; k < n_types; ++k)
         for (int a = 0; a < n_types; ++a) G.g[k * KP + a] = (a == k) ? 0.f : -host_gram[k * n_types + a];
-    // tile size / gather unroll: production default first, the others are tuning variants (FDB_SWEEP_VARIANT)
+    // FDB_SWEEP_VARIANT=5 forces the fp32-gather kernel (tests compare the two)
     static const int variant = getenv("FDB_SWEEP_VARIANT") ? atoi(getenv("FDB_SWEEP_VARIANT")) : 0;
     auto go = [&](auto kern, int nw) -> int {
         const size_t smem = (size_t)nw * 32 * 2 * TileLayout<KP>::S * 4 + (size_t)nw * kIdxCap * 4;
@@ -890,49 +330,9 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
         for (int k = 0; k < n_types; ++k) mean_diag += host_gram[k * n_types + k];
         mean_diag /= (float)n_types;
         const bool weak_coupling = lam * 8.f <= 0.02f * mean_diag;
-        if (plan != nullptr && ((variant == 0 && weak_coupling) || variant == 4 || variant == 6)) {
-            // halo-staged fp16 gather tile, 128-spot patches (4 warps); residency by row width: 6 CTAs/SM at 36 KB
-            // (Kp <= 32), 4 at 47 KB (Kp = 40), 3 at 56-70 KB (Kp >= 48)
-            constexpr int NWH = 4;
-            constexpr int MINB = KP <= 32 ? 6 : 3;
-            constexpr int tile = NWH * 32;
-            const int64_t n_ctas = ceil_div(n_rows, tile);
-            const char *pbase = (const char *)plan;
-            PlanView pv;
-            pv.halo_cnt = (const int32_t *)(pbase + plan_off_cnt());
-            pv.halo_rows = (const int32_t *)(pbase + plan_off_rows(n_ctas));
-            pv.codes = (const uint16_t *)(pbase + plan_off_codes(n_ctas, tile));
-            pv.codes8 = (const uint8_t *)(pbase + plan_off_codes8(n_ctas, tile));
-            const size_t smem_rows = (size_t)tile * TileLayout<KP>::S * 4 + (size_t)2 * tile * (KP / 2) * 4;
-            if (variant == 0 || KP != 32)                  // production: persistent, pipelined, pair-step descent
-                return launch_sweep_p<KP>(h, G, n_types, beta_in, beta_out, indptr, indices, n_rows, lam, rho, tol,
-                                          finalize, state, plan, st);     // (comparison kernels: Kp = 32 only)
-            if constexpr (KP == 32) {
-            if (variant == 6) {                            // comparison: persistent, two spots per lane (12 warps/SM)
-                const size_t smem = smem_rows + (size_t)4 * kCodeRounds * 32 + (size_t)3 * tile * 4;
-                auto kern = bcd_sweep_d_kernel<KP, 6, 0>;
-                int resident = 0;
-                FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, 64, smem));
-                const int grid = (int)std::min<int64_t>(n_ctas, (int64_t)kNumSM * std::max(resident, 1));
-                kern<<<grid, 64, smem, st>>>(h, G, beta_in, beta_out, indptr, indices, pv, (int)n_rows, n_types,
-                                             lam, rho, tol, finalize, state, (int)n_ctas);
-                FDB_LAUNCH_CHECK("bcd_sweep_d_kernel");
-                return FDB_OK;
-            }
-            auto kern = bcd_sweep_h_kernel<KP, NWH, MINB>;  // comparison: one patch per CTA
-            const size_t smem = smem_rows + (size_t)NWH * kIdxCap * 2;
-            FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            static const int pf_env = getenv("FDB_SWEEP_PREFETCH") ? atoi(getenv("FDB_SWEEP_PREFETCH")) : -1;
-            int resident = 0;
-            FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, tile, smem));
-            const int pf_stride = pf_env >= 0 ? pf_env : kNumSM * std::max(resident, 1) / 2;   // half a wave ahead
-            kern<<<(int)n_ctas, tile, smem, st>>>(h, G, beta_in, beta_out, indptr, indices, pv, (int)n_rows,
-                                                  n_types, lam, rho, tol, finalize, state, pf_stride);
-            FDB_LAUNCH_CHECK("bcd_sweep_h_kernel");
-            return FDB_OK;
-            }
-        }
+        if (plan != nullptr && variant == 0 && weak_coupling)      // production: persistent, pipelined, pair-step descent
+            return launch_sweep_p<KP>(h, G, n_types, beta_in, beta_out, indptr, indices, n_rows, lam, rho, tol,
+                                      finalize, state, plan, st);
     }
     if constexpr (KP <= 32) {
         if (variant == 1) return go(bcd_sweep_kernel<KP, 4, 1>, 4);

@@ -54,6 +54,20 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
 
     if (*reinterpret_cast<volatile int *>(&state->converged)) return;      // uniform across the grid
 
+    // Range of the fp16 gather tile.  Every |beta_in| is at most last_max_abs + last_max_diff (max|beta| of the sweep
+    // before plus the largest step it took; fdb_bcd_init seeds 1/K), so with 2^x <= bound < 2^(x+1) the tile stores
+    // beta * 2^(8-x): magnitudes below 512, sums of up to 64 neighbours below 32768 < 65504, and values down to
+    // 1e-7 of the largest one keep all 11 bits.  Powers of two: results are bit-identical to an unscaled tile whenever
+    // that one neither overflows nor underflows.  lam_s folds the factor back in.
+    float inv_s, lam_s;
+    {
+        const float bound = *reinterpret_cast<volatile float *>(&state->last_max_abs) +
+                            *reinterpret_cast<volatile float *>(&state->last_max_diff);
+        const int ef = min(max((int)((__float_as_uint(bound) >> 23) & 255u), 9), 245);
+        inv_s = __uint_as_float((unsigned)(262 - ef) << 23);
+        lam_s = lam * __uint_as_float((unsigned)(ef - 8) << 23);
+    }
+
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wrow = warp * 32;
     const int own = wrow + lane;
@@ -125,7 +139,7 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
         asm volatile("cp.async.wait_all;");
         __syncthreads();                 // (1) every warp is past the gather of the previous patch: g_tile is free
         auto to_gather = [&](int grow, int q, const float4 bb) {
-            const __half2 lo = __floats2half2_rn(bb.x, bb.y), hi = __floats2half2_rn(bb.z, bb.w);
+            const __half2 lo = __floats2half2_rn(bb.x * inv_s, bb.y * inv_s), hi = __floats2half2_rn(bb.z * inv_s, bb.w * inv_s);
             uint2 pk;
             pk.x = *reinterpret_cast<const uint32_t *>(&lo);
             pk.y = *reinterpret_cast<const uint32_t *>(&hi);
@@ -184,8 +198,8 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
 #pragma unroll
                 for (int q = 0; q < Q; ++q) {
                     const float4 v = ld4(src + 4 * q);
-                    acc[2 * q] = __hadd2(acc[2 * q], __floats2half2_rn(v.x, v.y));
-                    acc[2 * q + 1] = __hadd2(acc[2 * q + 1], __floats2half2_rn(v.z, v.w));
+                    acc[2 * q] = __hadd2(acc[2 * q], __floats2half2_rn(v.x * inv_s, v.y * inv_s));
+                    acc[2 * q + 1] = __hadd2(acc[2 * q + 1], __floats2half2_rn(v.z * inv_s, v.w * inv_s));
                 }
             };
             if (staged) {
@@ -206,6 +220,22 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
                     if (u < my_deg) code = plan.codes[my_s + u];
                     if (code == kCodeSlow) { add_slow(u); code = kCodeZero8; }
                     add_row((int)code);
+                    if ((u & 63) == 63 && u + 1 < maxdeg) {
+                        // 64 neighbours summed: move the half-precision partial sums into the fp32 H row (which has to have
+                        // landed first) so that very high degrees cannot overflow the accumulator
+                        asm volatile("cp.async.wait_all;");
+                        __syncwarp();
+#pragma unroll
+                        for (int q = 0; q < Q; ++q) {
+                            float4 c4 = ld4(c_tile + L::at(own, q));
+                            const float2 s01 = __half22float2(acc[2 * q]), s23 = __half22float2(acc[2 * q + 1]);
+                            c4.x = fmaf(lam_s, s01.x, c4.x); c4.y = fmaf(lam_s, s01.y, c4.y);
+                            c4.z = fmaf(lam_s, s23.x, c4.z); c4.w = fmaf(lam_s, s23.y, c4.w);
+                            st4(c_tile + L::at(own, q), c4);
+                            acc[2 * q] = __floats2half2_rn(0.f, 0.f);
+                            acc[2 * q + 1] = __floats2half2_rn(0.f, 0.f);
+                        }
+                    }
                 }
             }
         }
@@ -243,8 +273,8 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
                     const float den0 = G.diag[k0] + lam_deg, den1 = G.diag[k0 + 1] + lam_deg;
                     const float ri0 = den0 > 1e-10f ? rcp_fast(den0) : 0.f;      // core/solver.py:87-90
                     const float ri1 = den1 > 1e-10f ? rcp_fast(den1) : 0.f;
-                    u64 a0 = pack2(fmaf(lam, elem(ns4, k0 & 3), elem(c4, k0 & 3)),
-                                   fmaf(lam, elem(ns4, (k0 & 3) + 1), elem(c4, (k0 & 3) + 1)));
+                    u64 a0 = pack2(fmaf(lam_s, elem(ns4, k0 & 3), elem(c4, k0 & 3)),
+                                   fmaf(lam_s, elem(ns4, (k0 & 3) + 1), elem(c4, (k0 & 3) + 1)));
                     u64 a1 = pack2(neg_rho, neg_rho);
                     static_for<2, KP>([&](auto ic) {
                         constexpr int i = decltype(ic)::value;

@@ -194,410 +194,7 @@ sketch_contract_kernel(const IndPtr *__restrict__ indptr, const int32_t *__restr
     }
 }
 
-// ------------------------------------------------------------------------------------
-// fused form, v2 (fallback when the selected-gene count is unknown or the tables do not fit): same result as sketch_contract_kernel with ~5x fewer instructions.
-//   * per-gene bucket table lives in shared memory as u16 (0xFFFF = gene not selected), so the
-//     82 % of non-zeros that belong to unselected genes cost one LDS and no global lookup;
-//   * pass 1 streams the row, sums the library size and COMPACTS the selected entries
-//     (count, weight, bucket) into a per-warp shared list with ballot/popc;
-//   * pass 2 is lane-parallel over the compacted list: each lane owns whole entries and adds
-//     c_e * X_s^T[bucket_e, 0:Kp] into private registers (8 LDS.128 + 32 FFMA per entry for Kp = 32);
-//   * a shuffle butterfly transposes/reduces the 32 x Kp partials so lane k ends with H[i, k].
-// X_s^T rows are padded to XR = NK*32 + 4 floats so that random-row 128-bit reads spread over banks.
-// ------------------------------------------------------------------------------------
-constexpr int kListCap = 256;       // compacted selected entries per flush
-
-template <int NK>
-__device__ __forceinline__ void lane_reduce_transpose(float (&hv)[NK * 32], int lane)
-{
-    // after the call hv[0] (and hv[1] for NK == 2 -> types lane and lane + 32) hold the column sums
-#pragma unroll
-    for (int half = 0; half < NK; ++half) {
-        float *v = hv + half * 32;
-#pragma unroll
-        for (int s = 16; s >= 1; s >>= 1) {
-            const bool upper = (lane & s) != 0;
-#pragma unroll
-            for (int i = 0; i < s; ++i) {
-                const float send = upper ? v[i] : v[i + s];
-                const float keep = upper ? v[i + s] : v[i];
-                v[i] = keep + __shfl_xor_sync(kFull, send, s);
-            }
-        }
-    }
-    if (NK == 2) hv[1] = hv[32];
-}
-
-template <typename IndPtr, int NK>
-__global__ void __launch_bounds__(512, 1)
-sketch_contract_v2_kernel(const IndPtr *__restrict__ indptr, const int32_t *__restrict__ indices,
-                          const float *__restrict__ counts, int64_t n_spots, int n_genes,
-                          const int32_t *__restrict__ gene_bucket, const float *__restrict__ gene_weight,
-                          int d, const float *__restrict__ x_sketch_t, int kp,
-                          const int32_t *__restrict__ row_map, const int32_t *__restrict__ row_ids,
-                          float *__restrict__ h, float *__restrict__ ysq, int linear)
-{
-    constexpr int XR = NK * 32 + 4;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int warps_per_cta = blockDim.x >> 5;
-    float *xs = reinterpret_cast<float *>(smem_raw);                                   // d x XR
-    float *warp_base = xs + (size_t)d * XR + (size_t)warp * (d + 2 * kListCap + kListCap / 2);
-    float *acc = warp_base;                                                            // d
-    float *list_v = acc + d;                                                           // kListCap
-    float *list_w = list_v + kListCap;                                                 // kListCap
-    unsigned short *list_b = reinterpret_cast<unsigned short *>(list_w + kListCap);    // kListCap (u16)
-    unsigned short *gb16 = reinterpret_cast<unsigned short *>(
-        xs + (size_t)d * XR + (size_t)warps_per_cta * (d + 2 * kListCap + kListCap / 2));   // n_genes
-
-    for (int i = threadIdx.x; i < d * XR; i += blockDim.x) {
-        const int r = i / XR, c = i - r * XR;
-        xs[i] = c < kp ? __ldg(x_sketch_t + (size_t)r * kp + c) : 0.f;
-    }
-    for (int g = threadIdx.x; g < n_genes; g += blockDim.x) {
-        const int b = __ldg(gene_bucket + g);
-        gb16[g] = b >= 0 ? (unsigned short)b : (unsigned short)0xFFFF;
-    }
-    for (int c = lane; c < d; c += 32) acc[c] = 0.f;
-    __syncthreads();
-
-    unsigned lt_mask;
-    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
-
-    for (int64_t it = (int64_t)blockIdx.x * warps_per_cta + warp; it < n_spots;
-         it += (int64_t)gridDim.x * warps_per_cta) {
-        const int64_t row = row_ids ? (int64_t)__ldg(row_ids + it) : it;       // input row processed by this warp
-        const int64_t s = load_ptr(indptr, row), e = load_ptr(indptr, row + 1);
-        float hv[NK * 32];
-#pragma unroll
-        for (int i = 0; i < NK * 32; ++i) hv[i] = 0.f;
-
-        // lane-parallel AXPY over list[0, n) with the row's scale
-        auto flush = [&](int n, float scale) {
-            for (int t0 = 0; t0 < n; t0 += 32) {
-                const int t = t0 + lane;
-                if (t < n) {
-                    const int b = list_b[t];
-                    const float c = xform_value(list_v[t], scale) * list_w[t];
-                    atomicAdd(acc + b, c);
-                    const float4 *xr = reinterpret_cast<const float4 *>(xs + b * XR);
-#pragma unroll
-                    for (int q = 0; q < NK * 8; ++q) {
-                        const float4 x = xr[q];
-                        hv[4 * q] = fmaf(c, x.x, hv[4 * q]);
-                        hv[4 * q + 1] = fmaf(c, x.y, hv[4 * q + 1]);
-                        hv[4 * q + 2] = fmaf(c, x.z, hv[4 * q + 2]);
-                        hv[4 * q + 3] = fmaf(c, x.w, hv[4 * q + 3]);
-                    }
-                }
-            }
-        };
-        // stream [j_lo, j_hi): compact selected entries behind `cnt`; returns their count-sum (library part)
-        auto stream = [&](int64_t j_lo, int64_t j_hi, int &cnt, bool store, float scale, bool flush_when_full) {
-            float lib = 0.f;
-            for (int64_t j0 = j_lo; j0 < j_hi; j0 += 128) {
-                int g[4];
-                float v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int64_t j = j0 + 32 * u + lane;
-                    g[u] = j < j_hi ? ld_stream(indices + j) : -1;
-                    v[u] = j < j_hi ? ld_stream(counts + j) : 0.f;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (j0 + 32 * u >= j_hi) break;                         // warp-uniform
-                    const unsigned b = g[u] >= 0 ? gb16[g[u]] : 0xFFFFu;
-                    const bool sel = b != 0xFFFFu;
-                    const unsigned m = __ballot_sync(kFull, sel);
-                    if (flush_when_full && cnt + 32 > kListCap) {
-                        __syncwarp();
-                        flush(cnt, scale);
-                        __syncwarp();
-                        cnt = 0;
-                    }
-                    if (sel) {
-                        lib += v[u];
-                        const int pos = cnt + __popc(m & lt_mask);
-                        if (store && pos < kListCap) {
-                            list_v[pos] = v[u];
-                            list_w[pos] = __ldg(gene_weight + g[u]);
-                            list_b[pos] = (unsigned short)b;
-                        }
-                    }
-                    cnt += __popc(m);
-                }
-            }
-            return lib;
-        };
-
-        int cnt = 0;
-        float lib = warp_sum(stream(s, e, cnt, true, 0.f, false));
-        if (lib == 0.f) lib = 1.f;
-        const float scale = linear ? -1.f : 1e4f / lib;
-        __syncwarp();
-        if (cnt <= kListCap) {
-            flush(cnt, scale);
-        } else {                                   // rare: more selected entries than the list holds -> re-stream
-            int c2 = 0;
-            stream(s, e, c2, true, scale, true);
-            __syncwarp();
-            flush(c2, scale);
-        }
-        __syncwarp();
-        lane_reduce_transpose<NK>(hv, lane);
-
-        float sq = 0.f;
-        for (int c = lane * 4; c < d; c += 128) {
-            const float4 a = *reinterpret_cast<float4 *>(acc + c);
-            *reinterpret_cast<float4 *>(acc + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-            sq = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, sq))));
-        }
-        sq = warp_sum(sq);
-        const int64_t orow = row_map ? (int64_t)__ldg(row_map + row) : it;
-        float *out = h + orow * kp;
-        if (lane < kp) out[lane] = hv[0];
-        if (NK == 2 && 32 + lane < kp) out[32 + lane] = hv[1];
-        if (lane == 0) ysq[orow] = sq;
-        __syncwarp();
-    }
-}
-
-// ------------------------------------------------------------------------------------
-// fused form, v3 (production when the number of selected genes is known): v2 plus
-//   * NO global table lookups while streaming: a u16 gene -> slot table and a slot -> (bucket, weight)
-//     table are built in shared memory by each CTA (block scan over the gene axis), so the dependent
-//     index -> weight L2 round trip of v2 is gone;
-//   * cross-row software pipelining: the first 512 entries of the NEXT row are loaded into registers
-//     before the lane-parallel AXPY of the current row runs, so each warp always has 16 coalesced
-//     128-byte loads in flight (16 warps/SM x 16 x 128 B x 2 arrays = 64 KB per SM).
-// ------------------------------------------------------------------------------------
 constexpr int kPrefetch = 16;       // register-prefetched chunks of 32 entries (first 512 entries of a row)
-
-template <typename IndPtr, int NK>
-__global__ void __launch_bounds__(512, 1)
-sketch_contract_v3_kernel(const IndPtr *__restrict__ indptr, const int32_t *__restrict__ indices,
-                          const float *__restrict__ counts, int64_t n_spots, int n_genes, int n_selected,
-                          const int32_t *__restrict__ gene_bucket, const float *__restrict__ gene_weight,
-                          int d, const float *__restrict__ x_sketch_t, int kp,
-                          const int32_t *__restrict__ row_map, const int32_t *__restrict__ row_ids,
-                          float *__restrict__ h, float *__restrict__ ysq, int linear)
-{
-    constexpr int XR = NK * 32 + 4;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    const int warps_per_cta = blockDim.x >> 5;
-    const int per_warp_floats = d + kListCap + kListCap / 2;
-    float *xs = reinterpret_cast<float *>(smem_raw);                                    // d x XR
-    int2 *slot_bw = reinterpret_cast<int2 *>(xs + (size_t)d * XR);                      // n_selected (bucket, weight bits)
-    float *warp_base = reinterpret_cast<float *>(slot_bw + ((n_selected + 1) & ~1)) + (size_t)warp * per_warp_floats;
-    float *acc = warp_base;                                                             // d
-    float *list_v = acc + d;                                                            // kListCap
-    unsigned short *list_s = reinterpret_cast<unsigned short *>(list_v + kListCap);     // kListCap (u16 slots)
-    unsigned short *gslot = reinterpret_cast<unsigned short *>(
-        reinterpret_cast<float *>(slot_bw + ((n_selected + 1) & ~1)) + (size_t)warps_per_cta * per_warp_floats);
-    __shared__ int scan_warp[32];
-
-    for (int i = threadIdx.x; i < d * XR; i += blockDim.x) {
-        const int r = i / XR, c = i - r * XR;
-        xs[i] = c < kp ? __ldg(x_sketch_t + (size_t)r * kp + c) : 0.f;
-    }
-    for (int c = lane; c < d; c += 32) acc[c] = 0.f;
-    {   // gene -> slot (rank among selected genes): block-wide exclusive scan over contiguous gene chunks
-        const int per = (n_genes + (int)blockDim.x - 1) / (int)blockDim.x;
-        const int g0 = min((int)threadIdx.x * per, n_genes), g1 = min(g0 + per, n_genes);
-        int mine = 0;
-        for (int g = g0; g < g1; ++g) mine += __ldg(gene_bucket + g) >= 0;
-        int inc = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(kFull, inc, o);
-            if (lane >= o) inc += t;
-        }
-        if (lane == 31) scan_warp[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            int w = lane < warps_per_cta ? scan_warp[lane] : 0;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(kFull, w, o);
-                if (lane >= o) w += t;
-            }
-            scan_warp[lane] = w;
-        }
-        __syncthreads();
-        int slot = (warp ? scan_warp[warp - 1] : 0) + inc - mine;
-        for (int g = g0; g < g1; ++g) {
-            const int b = __ldg(gene_bucket + g);
-            unsigned short code = 0xFFFF;
-            if (b >= 0 && slot < n_selected && slot < 0xFFFF) {
-                slot_bw[slot] = make_int2(b, __float_as_int(__ldg(gene_weight + g)));
-                code = (unsigned short)slot;
-                ++slot;
-            }
-            gslot[g] = code;
-        }
-    }
-    __syncthreads();
-
-    unsigned lt_mask;
-    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
-    const int64_t stride = (int64_t)gridDim.x * warps_per_cta;
-
-    // lane-parallel AXPY over list[0, n) with the row's scale
-    float hv[NK * 32];
-    auto flush = [&](int n, float scale) {
-        for (int t0 = 0; t0 < n; t0 += 32) {
-            const int t = t0 + lane;
-            if (t < n) {
-                const int2 bw = slot_bw[list_s[t]];
-                const float c = xform_value(list_v[t], scale) * __int_as_float(bw.y);
-                atomicAdd(acc + bw.x, c);
-                const float4 *xr = reinterpret_cast<const float4 *>(xs + bw.x * XR);
-#pragma unroll
-                for (int q = 0; q < NK * 8; ++q) {
-                    const float4 x = xr[q];
-                    hv[4 * q] = fmaf(c, x.x, hv[4 * q]);
-                    hv[4 * q + 1] = fmaf(c, x.y, hv[4 * q + 1]);
-                    hv[4 * q + 2] = fmaf(c, x.z, hv[4 * q + 2]);
-                    hv[4 * q + 3] = fmaf(c, x.w, hv[4 * q + 3]);
-                }
-            }
-        }
-    };
-    // one chunk of 32 entries: look the slot up, add to the library size, append selected entries to the list
-    auto take = [&](int g, float v, int &cnt, float &lib, float scale, bool flush_when_full) {
-        const unsigned sl = g >= 0 ? gslot[g] : 0xFFFFu;
-        const bool sel = sl != 0xFFFFu;
-        const unsigned m = __ballot_sync(kFull, sel);
-        if (flush_when_full && cnt + 32 > kListCap) {
-            __syncwarp();
-            flush(cnt, scale);
-            __syncwarp();
-            cnt = 0;
-        }
-        if (sel) {
-            lib += v;
-            const int pos = cnt + __popc(m & lt_mask);
-            if (pos < kListCap) {
-                list_v[pos] = v;
-                list_s[pos] = (unsigned short)sl;
-            }
-        }
-        cnt += __popc(m);
-    };
-    auto row_of = [&](int64_t it) { return row_ids ? (int64_t)__ldg(row_ids + it) : it; };
-
-    // 32-bit offsets inside a row (rows longer than 2^31 entries are rejected on the host)
-    int64_t it = (int64_t)blockIdx.x * warps_per_cta + warp;
-    int pg[kPrefetch];
-    float pv[kPrefetch];
-    int64_t s = 0, row = 0;
-    int len = 0;
-    if (it < n_spots) {
-        row = row_of(it);
-        s = load_ptr(indptr, row);
-        len = (int)(load_ptr(indptr, row + 1) - s);
-    }
-    {
-        const int32_t *ip = indices + s;
-        const float *vp = counts + s;
-#pragma unroll
-        for (int u = 0; u < kPrefetch; ++u) {
-            const int j = 32 * u + lane;
-            pg[u] = j < len ? ld_stream(ip + j) : -1;
-            pv[u] = j < len ? ld_stream(vp + j) : 0.f;
-        }
-    }
-    while (it < n_spots) {
-        const int64_t it_next = it + stride;
-        int64_t s2 = 0, row2 = 0;
-        int len2 = 0;
-        if (it_next < n_spots) {
-            row2 = row_of(it_next);
-            s2 = load_ptr(indptr, row2);
-            len2 = (int)(load_ptr(indptr, row2 + 1) - s2);
-        }
-#pragma unroll
-        for (int i = 0; i < NK * 32; ++i) hv[i] = 0.f;
-        int cnt = 0;
-        float lib = 0.f;
-#pragma unroll
-        for (int u = 0; u < kPrefetch; ++u) {
-            if (32 * u >= len) break;                                     // warp-uniform
-            take(pg[u], pv[u], cnt, lib, 0.f, false);
-        }
-        {
-            const int32_t *ip = indices + s;
-            const float *vp = counts + s;
-            for (int j0 = 32 * kPrefetch; j0 < len; j0 += 128) {          // long rows: the rest, 4 chunks at a time
-                int g[4];
-                float v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int j = j0 + 32 * u + lane;
-                    g[u] = j < len ? ld_stream(ip + j) : -1;
-                    v[u] = j < len ? ld_stream(vp + j) : 0.f;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (j0 + 32 * u >= len) break;
-                    take(g[u], v[u], cnt, lib, 0.f, false);
-                }
-            }
-        }
-        lib = warp_sum(lib);
-        if (lib == 0.f) lib = 1.f;
-        const float scale = linear ? -1.f : 1e4f / lib;
-        const bool overflow = cnt > kListCap;
-        // next row's first 512 entries start streaming now and land while this row's AXPY runs
-        {
-            const int32_t *ip = indices + s2;
-            const float *vp = counts + s2;
-#pragma unroll
-            for (int u = 0; u < kPrefetch; ++u) {
-                const int j = 32 * u + lane;
-                pg[u] = j < len2 ? ld_stream(ip + j) : -1;
-                pv[u] = j < len2 ? ld_stream(vp + j) : 0.f;
-            }
-        }
-        __syncwarp();
-        if (!overflow) {
-            flush(cnt, scale);
-        } else {                                   // rare: more selected entries than the list holds -> re-stream
-            int c2 = 0;
-            float dummy = 0.f;
-            const int32_t *ip = indices + s;
-            const float *vp = counts + s;
-            for (int j0 = 0; j0 < len; j0 += 32) {
-                const int j = j0 + lane;
-                const int g = j < len ? ld_stream(ip + j) : -1;
-                const float v = j < len ? ld_stream(vp + j) : 0.f;
-                take(g, v, c2, dummy, scale, true);
-            }
-            __syncwarp();
-            flush(c2, scale);
-        }
-        __syncwarp();
-        lane_reduce_transpose<NK>(hv, lane);
-        float sq = 0.f;
-        for (int c = lane * 4; c < d; c += 128) {
-            const float4 a = *reinterpret_cast<float4 *>(acc + c);
-            *reinterpret_cast<float4 *>(acc + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-            sq = fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, fmaf(a.w, a.w, sq))));
-        }
-        sq = warp_sum(sq);
-        const int64_t orow = row_map ? (int64_t)__ldg(row_map + row) : it;
-        float *out = h + orow * kp;
-        if (lane < kp) out[lane] = hv[0];
-        if (NK == 2 && 32 + lane < kp) out[32 + lane] = hv[1];
-        if (lane == 0) ysq[orow] = sq;
-        __syncwarp();
-        it = it_next; s = s2; len = len2; row = row2;
-    }
-}
 
 // ------------------------------------------------------------------------------------
 // fused form, v5 (production): the v3 structure (one row per warp, u16 gene -> slot table, cross-row register
@@ -1125,8 +722,7 @@ static int launch_fused(const void *indptr, const int32_t *indices, const float 
                         const int32_t *row_ids, float *h, float *ysq, int linear, cudaStream_t st)
 {
     // production: v5 (v3 structure + conflict-free XOR-phased AXPY, select-free reduction, integer atomics)
-    if (n_selected >= 0 && n_selected < 0xFFFF && getenv("FDB_SKETCH_V1") == nullptr && getenv("FDB_SKETCH_V2") == nullptr &&
-        getenv("FDB_SKETCH_V3") == nullptr) {
+    if (n_selected >= 0 && n_selected < 0xFFFF && getenv("FDB_SKETCH_V1") == nullptr) {
         const size_t fixed = (size_t)d * NK * 128 + (size_t)((n_selected + 1) & ~1) * 8 + (size_t)(n_genes + 1) * 2 + 16 + 128;
         const size_t per_warp = (size_t)d * 4 + kV5List * 8;
         int warps = 0;
@@ -1144,44 +740,6 @@ static int launch_fused(const void *indptr, const int32_t *indices, const float 
                 return FDB_OK;
             };
             return linear ? go(sketch_contract_v5_kernel<IndPtr, NK, false>) : go(sketch_contract_v5_kernel<IndPtr, NK, true>);
-        }
-    }
-    // previous: v3 (gene->slot and slot->(bucket, weight) tables + compaction lists in shared memory)
-    if (n_selected >= 0 && n_selected < 0xFFFF && getenv("FDB_SKETCH_V1") == nullptr && getenv("FDB_SKETCH_V2") == nullptr) {
-        constexpr int XR = NK * 32 + 4;
-        const size_t fixed = (size_t)d * XR * 4 + (size_t)((n_selected + 1) & ~1) * 8 + (size_t)n_genes * 2 + 16;
-        const size_t per_warp = ((size_t)d + kListCap + kListCap / 2) * 4;
-        int warps = 0;
-        for (int w : {16, 12, 8, 4})
-            if (fixed + w * per_warp <= 227 * 1024) { warps = w; break; }
-        if (warps) {
-            const size_t smem = fixed + warps * per_warp;
-            auto kern = sketch_contract_v3_kernel<IndPtr, NK>;
-            FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const int grid = pick_grid(n_spots, warps, 1);
-            kern<<<grid, warps * 32, smem, st>>>((const IndPtr *)indptr, indices, counts, n_spots, n_genes, n_selected,
-                                                 gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, linear);
-            FDB_LAUNCH_CHECK("sketch_contract_v3_kernel");
-            return FDB_OK;
-        }
-    }
-    // next: v2 (bucket table + compaction lists in shared memory, weights from L2)
-    {
-        constexpr int XR = NK * 32 + 4;
-        const size_t fixed = (size_t)d * XR * 4 + (size_t)n_genes * 2 + 16;
-        const size_t per_warp = ((size_t)d + 2 * kListCap + kListCap / 2) * 4;
-        int warps = 0;
-        for (int w : {16, 12, 8, 4})
-            if (fixed + w * per_warp <= 227 * 1024) { warps = w; break; }
-        if (warps && d <= 65535 && getenv("FDB_SKETCH_V1") == nullptr) {
-            const size_t smem = fixed + warps * per_warp;
-            auto kern = sketch_contract_v2_kernel<IndPtr, NK>;
-            FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const int grid = pick_grid(n_spots, warps, 1);
-            kern<<<grid, warps * 32, smem, st>>>((const IndPtr *)indptr, indices, counts, n_spots, n_genes,
-                                                 gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, linear);
-            FDB_LAUNCH_CHECK("sketch_contract_v2_kernel");
-            return FDB_OK;
         }
     }
     // fallback: v1 (tables in global memory) for very wide gene axes / sketches

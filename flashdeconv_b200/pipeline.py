@@ -21,6 +21,7 @@ from . import _native
 from ._native import check, lib
 
 GRAPH_MODES = {"knn": 0, "radius": 1, "grid": 2}
+MAX_TYPES = 64                   # FDB_MAX_TYPES in include/fdb200.h
 
 
 def _ptr(t):
@@ -254,8 +255,11 @@ class DevicePath:
         t = self.torch
         self.gene_bucket = t.from_numpy(tables.gene_bucket).to(self.dev)
         self.gene_weight = t.from_numpy(tables.gene_weight).to(self.dev)
-        xst = np.zeros((tables.d, self.Kp), dtype=np.float32)
-        xst[:, : self.K] = tables.X_sketch.T
+        # the kernels move sketch rows as 16-byte vectors: the device-side sketch dimension is padded to a multiple of
+        # four with empty buckets (no gene maps to them, X_s^T rows are zero), which changes nothing in H or ||y_s||^2
+        self.d_dev = 4 * ((tables.d + 3) // 4)
+        xst = np.zeros((self.d_dev, self.Kp), dtype=np.float32)
+        xst[: tables.d, : self.K] = tables.X_sketch.T
         self.x_sketch_t = t.from_numpy(xst).to(self.dev)
         self.gram32 = np.ascontiguousarray(tables.gram, dtype=np.float32)
         n = csr.shape[0]
@@ -277,7 +281,7 @@ class DevicePath:
         row_map = self.graph.rank if self.graph is not None else None
         fn = lib.fdb_sketch_linear_contract_csr if tb.linear else lib.fdb_sketch_contract_csr
         check(fn(_ptr(c.indptr), int(c.indptr.dtype == self.torch.int64), _ptr(c.indices), _ptr(c.data), c.shape[0],
-                 c.shape[1], _ptr(self.gene_bucket), _ptr(self.gene_weight), tb.d, _ptr(self.x_sketch_t), self.K,
+                 c.shape[1], _ptr(self.gene_bucket), _ptr(self.gene_weight), self.d_dev, _ptr(self.x_sketch_t), self.K,
                  _ptr(row_map), _ptr(None), int(len(tb.bucket)), _ptr(self.h), _ptr(self.ysq), _stream(self.torch)),
               "sketch_contract_csr")
 
@@ -354,7 +358,7 @@ class DevicePath:
 
         mark("graph", lambda: self.stage_graph(method, k, radius))
         mark("sketch", self.stage_sketch)
-        lam_used = self.lambda_auto() if isinstance(lam, str) else float(lam)
+        lam_used = self.lambda_auto() if (isinstance(lam, str) and lam == "auto") else float(lam)
         rho_s = self.rho_scaled(rho)
         mark("solve", lambda: self.stage_solve(lam_used, rho_s, max_iter, tol))
         n_iter, conv, rel = self.read_state()
@@ -375,7 +379,7 @@ class DevicePath:
         n = self.csr.shape[0]
         self.stage_graph(method, k, radius)
         self.stage_sketch()
-        lam_used = self.lambda_auto() if isinstance(lam, str) else float(lam)
+        lam_used = self.lambda_auto() if (isinstance(lam, str) and lam == "auto") else float(lam)   # core/deconv.py:370-377
         rho_s = self.rho_scaled(rho)
         objectives = []
         if verbose:

@@ -88,6 +88,57 @@ def make_dataset(n_spots=1000, n_genes=500, n_types=5, depth=2000.0, jitter=0.1,
     return SyntheticData(Y=Y, X=X, coords=coords, beta_true=beta)
 
 
+def make_dataset_sparse(n_spots, n_genes, n_types, depth, jitter=0.1, seed=0, chunk=25_000, threads=None):
+    """Host (numpy) generator for LARGE sparse shapes: the same statistical model as `make_dataset`, sampled molecule by
+    molecule so that the cost is O(total counts) instead of O(N x G) -- T_i ~ Poisson(depth_i) molecules per spot, each
+    with a type ~ beta_i and a gene ~ the type's profile (equivalent to independent Poisson(depth_i * (beta_i Xp)_g)
+    counts).  Chunks are drawn by a thread pool from spawned seed sequences: deterministic for a given (seed, chunk)
+    whatever the thread count.  Returns a dict of numpy arrays: indptr int64, indices int32, data float32, coords, X,
+    beta_true, shape.  1M x 18k at depth 400 takes ~1 minute on 8 cores."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    rng = np.random.default_rng(seed)
+    X = _signatures(rng, n_types, n_genes)
+    coords, side = _coords(rng, n_spots, jitter)
+    beta = _mixing(rng, coords, side, n_types)
+    spot_depth = rng.gamma(shape=5.0, scale=depth / 5.0, size=n_spots)
+    cdf = np.cumsum(X / X.sum(1, keepdims=True), axis=1)
+    cdf /= cdf[:, -1:]
+    cdf_flat = (cdf + np.arange(n_types)[:, None]).ravel()              # type k occupies [k, k + 1)
+    n_chunks = (n_spots + chunk - 1) // chunk
+    seeds = np.random.SeedSequence(seed).spawn(max(n_chunks, 1))
+
+    def one(ci):
+        r = np.random.default_rng(seeds[ci])
+        lo, hi = ci * chunk, min((ci + 1) * chunk, n_spots)
+        T = r.poisson(spot_depth[lo:hi])
+        per_type = r.multinomial(T, beta[lo:hi])                        # molecules per (spot, type)
+        types = np.repeat(np.tile(np.arange(n_types), hi - lo), per_type.ravel())
+        spots = np.repeat(np.arange(hi - lo, dtype=np.int64), T)
+        genes = np.searchsorted(cdf_flat, r.random(types.size) + types, side="right") - types * n_genes
+        np.clip(genes, 0, n_genes - 1, out=genes)
+        key = spots * n_genes + genes
+        key.sort()
+        first = np.empty(key.size, dtype=bool)
+        first[:1] = True
+        np.not_equal(key[1:], key[:-1], out=first[1:])
+        starts = np.flatnonzero(first)
+        cnt = np.diff(np.append(starts, key.size)).astype(np.float32)
+        uk = key[starts]
+        rows = uk // n_genes
+        return np.bincount(rows, minlength=hi - lo), (uk - rows * n_genes).astype(np.int32), cnt
+
+    with ThreadPoolExecutor(threads or os.cpu_count() or 1) as ex:
+        parts = list(ex.map(one, range(n_chunks)))
+    indptr = np.zeros(n_spots + 1, dtype=np.int64)
+    if parts:
+        np.cumsum(np.concatenate([p[0] for p in parts]), out=indptr[1:])
+    cat = lambda i, dt: np.concatenate([p[i] for p in parts]) if parts else np.zeros(0, dtype=dt)
+    return dict(indptr=indptr, indices=cat(1, np.int32), data=cat(2, np.float32), coords=coords, X=X, beta_true=beta,
+                shape=(n_spots, n_genes))
+
+
 def make_dataset_device(n_spots, n_genes, n_types, depth, jitter=0.1, seed=0, chunk=32_768,
                         device="cuda", method=None, pinned=False):
     """CUDA-side generator for benchmark shapes.

@@ -168,6 +168,12 @@ class TiledPath:
             self.mode = "torch"
         self.comm = self._native_comm() if self.mode == "nccl" else None
 
+    @property
+    def mode_description(self) -> str:
+        return {"peer": "direct NVLink peer-memory row pushes + flag/max-norm hand-shake (no NCCL on the data path)",
+                "nccl": "ncclSend/ncclRecv + MAX all-reduce issued from the native loop",
+                "torch": "torch.distributed isend/irecv + all_reduce"}[self.mode]
+
     def _native_comm(self):
         """NCCL communicator owned by libfdb200 (the solve loop issues its collectives from C).  The unique id
         travels over the existing torch.distributed group; the communicator is created once per group and

@@ -46,6 +46,13 @@ int fdo_num_threads(void)
 #endif
 }
 
+/* explicit thread count (bench.py: torchrun exports OMP_NUM_THREADS=1 to its workers) */
+void fdo_set_num_threads(int n)
+{
+    if (n > 0) omp_set_num_threads(n);
+}
+
+
 /* One Jacobi sweep over all spots.  beta_prev is read-only; beta_next gets the
  * update.  diff_out / abs_out receive per-spot max|new-old| and max|old|.   */
 void fdo_bcd_sweep(const double *h_spot_major,   /* N x K  */

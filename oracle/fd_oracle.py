@@ -59,12 +59,20 @@ def _native():
         lib.fdo_sketch_csr.argtypes = [i64p, i32p, dp, ctypes.c_int64, i32p, dp, ctypes.c_int, dp]
         lib.fdo_sketch_csr.restype = None
         lib.fdo_num_threads.restype = ctypes.c_int
+        lib.fdo_set_num_threads.argtypes = [ctypes.c_int]
+        lib.fdo_set_num_threads.restype = None
         _lib = lib
     return _lib
 
 
 def native_threads() -> int:
     return int(_native().fdo_num_threads())
+
+
+def set_native_threads(n: int) -> int:
+    """Thread count of the C/OpenMP sweep (the numba prange of core/solver.py:149), whatever OMP_NUM_THREADS says."""
+    _native().fdo_set_num_threads(int(n))
+    return native_threads()
 
 
 def _p(a, ct):
