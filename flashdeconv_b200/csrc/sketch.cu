@@ -263,8 +263,11 @@ __device__ __forceinline__ float sk_xform(float v, float scale)
 
 constexpr int kV5List = 256;        // compacted selected entries per flush (8-byte records)
 
-template <typename IndPtr, int NK, bool FIXED>
-__global__ void __launch_bounds__(512, 1)
+// TAB = true: u16 gene -> slot table (2 bytes per gene); TAB = false: one membership bit per gene + a rank prefix per
+// 32-gene word (slot = prefix + popc of the bits below), for wide gene axes / wide rows where the table does not fit
+// next to X_s^T -- the list then carries the gene and the slot is computed for the selected entries only.
+template <typename IndPtr, int NK, bool FIXED, bool TAB>
+__global__ void __launch_bounds__(NK == 1 ? 512 : 448, 1)               // wide rows: 64 accumulator registers per lane
 sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__restrict__ indices,
                           const float *__restrict__ counts, int64_t n_spots, int n_genes, int n_selected,
                           const int32_t *__restrict__ gene_bucket, const float *__restrict__ gene_weight,
@@ -289,7 +292,11 @@ sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
     unsigned char *warp_area = reinterpret_cast<unsigned char *>(slot_bw + ((n_selected + 1) & ~1));
     int *acc = reinterpret_cast<int *>(warp_area + (size_t)warp * per_warp_bytes);      // d words
     float2 *list = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(acc) + d * 4);   // (count, slot)
-    unsigned short *gslot = reinterpret_cast<unsigned short *>(warp_area + (size_t)warps_per_cta * per_warp_bytes);
+    unsigned char *tab_area = warp_area + (size_t)warps_per_cta * per_warp_bytes;
+    unsigned short *gslot = reinterpret_cast<unsigned short *>(tab_area);                           // TAB: n_genes + 1
+    const int nwords = (n_genes + 31) >> 5;
+    unsigned *bitmap = reinterpret_cast<unsigned *>(tab_area);                                       // !TAB: nwords + 1
+    unsigned *prefix = bitmap + nwords + 1;                                                          // !TAB: nwords + 1
     const unsigned list_addr = (unsigned)__cvta_generic_to_shared(list);
 
     for (int i = threadIdx.x; i < d * XS; i += blockDim.x) {
@@ -297,7 +304,8 @@ sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
         xs[i] = c < kp ? __ldg(x_sketch_t + (size_t)r * kp + c) : 0.f;
     }
     for (int c = lane; c < d; c += 32) acc[c] = 0;
-    {   // gene -> slot (rank among selected genes): block-wide exclusive scan over contiguous gene chunks
+    if (threadIdx.x == 0) s_wmax = 0.f;
+    if (TAB) {   // gene -> slot (rank among selected genes): block-wide exclusive scan over contiguous gene chunks
         const int per = (n_genes + (int)blockDim.x - 1) / (int)blockDim.x;
         const int g0 = min((int)threadIdx.x * per, n_genes), g1 = min(g0 + per, n_genes);
         int mine = 0;
@@ -309,7 +317,6 @@ sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
             if (lane >= o) inc += t;
         }
         if (lane == 31) scan_warp[warp] = inc;
-        if (threadIdx.x == 0) s_wmax = 0.f;
         __syncthreads();
         if (warp == 0) {
             int w = lane < warps_per_cta ? scan_warp[lane] : 0;
@@ -333,6 +340,55 @@ sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
             gslot[g] = code;
         }
         if (threadIdx.x == 0) gslot[n_genes] = 0xFFFF;                                  // the pad gene of masked lanes
+    } else {     // membership bitmap + rank prefix per word (word nwords stays empty: the pad gene of masked lanes)
+        unsigned lt;
+        asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lt));
+        for (int w = warp; w <= nwords; w += warps_per_cta) {
+            const int g = 32 * w + lane;
+            const bool sel = g < n_genes && __ldg(gene_bucket + g) >= 0;
+            const unsigned bits = __ballot_sync(kFull, sel);
+            if (lane == 0) { bitmap[w] = bits; prefix[w] = __popc(bits); }
+        }
+        __syncthreads();
+        const int n = nwords + 1;
+        const int per = (n + (int)blockDim.x - 1) / (int)blockDim.x;
+        const int w0 = min((int)threadIdx.x * per, n), w1 = min(w0 + per, n);
+        int tot = 0;
+        for (int w = w0; w < w1; ++w) tot += (int)prefix[w];
+        int inc = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(kFull, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) scan_warp[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = lane < warps_per_cta ? scan_warp[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(kFull, w, o);
+                if (lane >= o) w += t;
+            }
+            scan_warp[lane] = w;
+        }
+        __syncthreads();
+        int run = (warp ? scan_warp[warp - 1] : 0) + inc - tot;
+        for (int w = w0; w < w1; ++w) {
+            const int c = (int)prefix[w];
+            prefix[w] = (unsigned)run;
+            run += c;
+        }
+        __syncthreads();
+        for (int w = warp; w < nwords; w += warps_per_cta) {
+            const int g = 32 * w + lane;
+            const unsigned bits = bitmap[w];
+            const int slot = (int)prefix[w] + __popc(bits & lt);
+            const bool keep = ((bits >> lane) & 1u) && slot < n_selected;   // genes ranked past n_selected are dropped
+            if (keep) slot_bw[slot] = make_int2(__ldg(gene_bucket + g), __float_as_int(__ldg(gene_weight + g)));
+            const unsigned kept = __ballot_sync(kFull, keep);
+            if (lane == 0) bitmap[w] = kept;
+        }
     }
     __syncthreads();
     if (FIXED) {   // W = max over buckets of sum |w|: warp 0's accumulator as float scratch, then re-zeroed
@@ -364,7 +420,7 @@ sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
     const int64_t stride = (int64_t)gridDim.x * warps_per_cta;
     const int j8 = lane & 7;
     const unsigned xs_lane = base_addr + 16u * j8;
-    const int pad_gene = n_genes;
+    const int pad_gene = TAB ? n_genes : 32 * nwords;
 
     sk_u64 hv[NK * 16];                                                                 // NK x 8 chunk blocks (float pairs)
     // lane-parallel AXPY over list[0, n) with the row's scale
@@ -373,9 +429,14 @@ sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
         // iteration's eight row chunks, so the dependent LDS chain overlaps the FFMA2 block
         float2 rec = make_float2(0.f, 0.f);
         int2 bw = make_int2(0, 0);
+        auto slot_of = [&](float code) -> int {
+            const int x = __float_as_int(code);
+            if (TAB) return x;
+            return (int)prefix[x >> 5] + __popc(bitmap[x >> 5] & ((1u << (x & 31)) - 1u));
+        };
         if (lane < n) {
             rec = list[lane];
-            bw = slot_bw[__float_as_int(rec.y)];
+            bw = slot_bw[slot_of(rec.y)];
         }
 #pragma unroll 1
         for (int t0 = 0; t0 < n; t0 += 32) {
@@ -385,10 +446,11 @@ sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
             const int tn = t0 + 32 + lane;
             if (tn < n) {
                 rec = list[tn];
-                bw = slot_bw[__float_as_int(rec.y)];
+                bw = slot_bw[slot_of(rec.y)];
             }
             if (on) {
                 const float c = sk_xform(v, scale) * __int_as_float(cur.y);
+                reinterpret_cast<int *>(list)[2 * (t0 + lane) + 1] = cur.x;             // the read-back pass wants the bucket
                 if (FIXED) atomicAdd(acc + cur.x, __float2int_rn(c * q_scale));
                 else atomicAdd(reinterpret_cast<float *>(acc) + cur.x, c);
                 const unsigned a0 = xs_lane + (unsigned)cur.x * (XS * 4);
@@ -410,8 +472,16 @@ sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
     };
     // one chunk of 32 entries: look the slot up, add to the library size, append selected entries to the list
     auto take = [&](int g, float v, int &cnt, float &lib) {
-        const unsigned sl = gslot[g];
-        const bool sel = sl != 0xFFFFu;
+        unsigned sl;
+        bool sel;
+        if (TAB) {
+            sl = gslot[g];
+            sel = sl != 0xFFFFu;
+        } else {
+            const unsigned word = bitmap[g >> 5];
+            sl = (unsigned)g;
+            sel = (__funnelshift_r(word, word, g) & 1u) != 0u;
+        }
         const unsigned m = __ballot_sync(kFull, sel);
         const int pos = cnt + __popc(m & lt_mask);
         if (sel) {
@@ -446,6 +516,8 @@ sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
     }
     while (it < n_spots) {
         const int64_t it_next = it + stride;
+        // output row: loaded now so that the final store does not wait on a dependent global load
+        const int64_t orow = row_map ? (int64_t)__ldg(row_map + row) : it;
         int64_t s2 = 0, row2 = 0;
         int len2 = 0;
         if (it_next < n_spots) {
@@ -504,7 +576,7 @@ sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
             // bucket sums back: the first entry of a bucket to get there takes S_b and leaves 0
 #pragma unroll 1
             for (int t = lane; t < cnt; t += 32) {
-                const int b = slot_bw[__float_as_int(list[t].y)].x;
+                const int b = __float_as_int(list[t].y);
                 float sb;
                 if (FIXED) sb = (float)atomicExch(acc + b, 0) * q_inv;
                 else sb = atomicExch(reinterpret_cast<float *>(acc) + b, 0.f);
@@ -553,7 +625,6 @@ sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
             }
         }
         sq = warp_sum(sq);
-        const int64_t orow = row_map ? (int64_t)__ldg(row_map + row) : it;
         float *out = h + orow * kp;
         if (lane < 8) {                                                   // lane j: chunk j (and 8 + j) of H[orow]
             if (4 * lane < kp) {
@@ -721,15 +792,24 @@ static int launch_fused(const void *indptr, const int32_t *indices, const float 
                         const float *gene_weight, int d, const float *x_sketch_t, int kp, const int32_t *row_map,
                         const int32_t *row_ids, float *h, float *ysq, int linear, cudaStream_t st)
 {
-    // production: v5 (v3 structure + conflict-free XOR-phased AXPY, select-free reduction, integer atomics)
-    if (n_selected >= 0 && n_selected < 0xFFFF && getenv("FDB_SKETCH_V1") == nullptr) {
-        const size_t fixed = (size_t)d * NK * 128 + (size_t)((n_selected + 1) & ~1) * 8 + (size_t)(n_genes + 1) * 2 + 16 + 128;
+    // production: v5 (v3 structure + conflict-free XOR-phased AXPY, select-free reduction, integer atomics); the u16
+    // gene -> slot table when it leaves room for at least 12 warps, else the membership bitmap + rank prefix
+    if (n_selected >= 0 && getenv("FDB_SKETCH_V1") == nullptr) {
+        const int force_tab = getenv("FDB_SKETCH_TAB") ? atoi(getenv("FDB_SKETCH_TAB")) : -1;
+        const size_t common = (size_t)d * NK * 128 + (size_t)((n_selected + 1) & ~1) * 8 + 16 + 128;
         const size_t per_warp = (size_t)d * 4 + kV5List * 8;
-        int warps = 0;
-        for (int w : {16, 12, 8, 4})
-            if (fixed + w * per_warp <= 227 * 1024 - 256) { warps = w; break; }
+        const size_t limit = 227 * 1024 - 256;
+        auto warps_for = [&](size_t table_bytes) {
+            for (int w : {16, 14, 12, 10, 8, 6, 4})
+                if (w * 32 <= (NK == 1 ? 512 : 448) && common + table_bytes + w * per_warp <= limit) return w;
+            return 0;
+        };
+        const size_t tab_bytes = (size_t)(n_genes + 1) * 2, bit_bytes = (size_t)(((n_genes + 31) >> 5) + 1) * 8;
+        const int w_tab = n_selected < 0xFFFF ? warps_for(tab_bytes) : 0, w_bit = warps_for(bit_bytes);
+        const bool use_tab = force_tab >= 0 ? (force_tab != 0 && w_tab > 0) : (w_tab >= 12 || w_tab >= w_bit);
+        const int warps = use_tab ? w_tab : w_bit;
         if (warps) {
-            const size_t smem = fixed + warps * per_warp;
+            const size_t smem = common + (use_tab ? tab_bytes : bit_bytes) + warps * per_warp;
             const int grid = pick_grid(n_spots, warps, 1);
             auto go = [&](auto kern) -> int {
                 FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -739,7 +819,11 @@ static int launch_fused(const void *indptr, const int32_t *indices, const float 
                 FDB_LAUNCH_CHECK("sketch_contract_v5_kernel");
                 return FDB_OK;
             };
-            return linear ? go(sketch_contract_v5_kernel<IndPtr, NK, false>) : go(sketch_contract_v5_kernel<IndPtr, NK, true>);
+            if (use_tab)
+                return linear ? go(sketch_contract_v5_kernel<IndPtr, NK, false, true>)
+                              : go(sketch_contract_v5_kernel<IndPtr, NK, true, true>);
+            return linear ? go(sketch_contract_v5_kernel<IndPtr, NK, false, false>)
+                          : go(sketch_contract_v5_kernel<IndPtr, NK, true, false>);
         }
     }
     // fallback: v1 (tables in global memory) for very wide gene axes / sketches

@@ -110,12 +110,16 @@ def test_sketch_ragged_rows_vs_oracle(fo, n, G, d, density):
     (37, 600, 50, 512, 0.9, 1.0, ""),          # wide rows (Kp = 56) + every row overflows the list
     (5, 100, 3, 8, 0.5, 0.5, ""),              # fewer rows than one warp batch pair, tiny sketch
     (500, 2500, 40, 256, 0.1, 0.5, "FDB_SKETCH_V1"),
+    (300, 3000, 7, 512, 0.3, 1.0, "FDB_SKETCH_TAB=0"),      # membership bitmap + rank prefix instead of the u16 table
+    (500, 2500, 40, 256, 0.1, 0.5, "FDB_SKETCH_TAB=0"),
+    (1003, 18000, 30, 512, 0.02, 0.18, "FDB_SKETCH_TAB=0"),
+    (257, 25000, 40, 512, 0.01, 0.16, ""),                  # the C4 shape: wide rows + wide gene axis -> bitmap form
 ])
 def test_fused_sketch_ragged_vs_oracle(fo, monkeypatch, n, G, K, d, density, frac_sel, force):
     import torch
     from flashdeconv_b200 import pipeline as pl
     if force:
-        monkeypatch.setenv(force, "1")
+        monkeypatch.setenv(*(force.split("=") if "=" in force else (force, "1")))
     rng = np.random.default_rng(G + K)
     Y = sparse.random(n, G, density=density, format="csr", random_state=np.random.RandomState(K),
                       data_rvs=lambda s: rng.integers(1, 30, s).astype(np.float64))
