@@ -299,13 +299,28 @@ bcd_init_kernel(float *__restrict__ beta, int64_t n_rows, int kp, int n_types, S
 template <int KP>
 int launch_sweep_p(const float *h, const GramArg<KP> &G, int n_types, const float *beta_in, float *beta_out,
                    const int32_t *indptr, const int32_t *indices, int64_t n_rows, float lam, float rho, float tol,
-                   int finalize, SolveState *state, const void *plan, cudaStream_t st);
+                   int finalize, SolveState *state, const void *plan, cudaStream_t st, const SweepComm *comm);
+
+// fp16 neighbour values are admissible while the spatial term is a small part of the diagonal
+// (auto lambda: lam*deg = 0.5 % of G_kk); for strongly coupled problems the sweep stays in fp32
+static bool weak_coupling(const float *host_gram, int n_types, float lam)
+{
+    float mean_diag = 0.f;
+    for (int k = 0; k < n_types; ++k) mean_diag += host_gram[k * n_types + k];
+    mean_diag /= (float)n_types;
+    return lam * 8.f <= 0.02f * mean_diag;
+}
+static int sweep_variant()
+{
+    static const int variant = getenv("FDB_SWEEP_VARIANT") ? atoi(getenv("FDB_SWEEP_VARIANT")) : 0;
+    return variant;
+}
 
 template <int KP>
 static int launch_sweep(const float *h, const float *host_gram, int n_types, const float *beta_in,
                         float *beta_out, const int32_t *indptr, const int32_t *indices, int64_t n_rows,
                         float lam, float rho, float tol, int finalize, SolveState *state, const void *plan,
-                        cudaStream_t st)
+                        cudaStream_t st, const SweepComm *comm)
 {
     GramArg<KP> G;
     for (int i = 0; i < KP * KP; ++i) G.g[i] = 0.f;
@@ -313,7 +328,7 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
     for (int k = 0; k < n_types; ++k)
         for (int a = 0; a < n_types; ++a) G.g[k * KP + a] = (a == k) ? 0.f : -host_gram[k * n_types + a];
     // FDB_SWEEP_VARIANT=5 forces the fp32-gather kernel (tests compare the two)
-    static const int variant = getenv("FDB_SWEEP_VARIANT") ? atoi(getenv("FDB_SWEEP_VARIANT")) : 0;
+    const int variant = sweep_variant();
     auto go = [&](auto kern, int nw) -> int {
         const size_t smem = (size_t)nw * 32 * 2 * TileLayout<KP>::S * 4 + (size_t)nw * kIdxCap * 4;
         FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -324,15 +339,13 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
         return FDB_OK;
     };
     if constexpr (KP % 8 == 0) {
-        // fp16 neighbour values are admissible while the spatial term is a small part of the diagonal
-        // (auto lambda: lam*deg = 0.5 % of G_kk); for strongly coupled problems stay in fp32
-        float mean_diag = 0.f;
-        for (int k = 0; k < n_types; ++k) mean_diag += host_gram[k * n_types + k];
-        mean_diag /= (float)n_types;
-        const bool weak_coupling = lam * 8.f <= 0.02f * mean_diag;
-        if (plan != nullptr && variant == 0 && weak_coupling)      // production: persistent, pipelined, pair-step descent
+        if (plan != nullptr && variant == 0 && weak_coupling(host_gram, n_types, lam))      // production kernel
             return launch_sweep_p<KP>(h, G, n_types, beta_in, beta_out, indptr, indices, n_rows, lam, rho, tol,
-                                      finalize, state, plan, st);
+                                      finalize, state, plan, st, comm);
+    }
+    if (comm != nullptr) {
+        set_error("the fused multi-GPU sweep needs the gather plan and weak coupling");
+        return FDB_ERR_UNSUPPORTED;
     }
     if constexpr (KP <= 32) {
         if (variant == 1) return go(bcd_sweep_kernel<KP, 4, 1>, 4);
@@ -345,12 +358,12 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
 static int dispatch_sweep(const float *h, const float *host_gram, int n_types, const float *beta_in,
                           float *beta_out, const int32_t *indptr, const int32_t *indices, int64_t n_rows,
                           float lam, float rho, float tol, int finalize, SolveState *state, const void *plan,
-                          cudaStream_t st)
+                          cudaStream_t st, const SweepComm *comm = nullptr)
 {
 #define FDB_SWEEP_CASE(KP_)                                                                            \
     case KP_:                                                                                          \
         return launch_sweep<KP_>(h, host_gram, n_types, beta_in, beta_out, indptr, indices, n_rows,    \
-                                 lam, rho, tol, finalize, state, plan, st);
+                                 lam, rho, tol, finalize, state, plan, st, comm);
     switch (fdb_padded_types(n_types)) {
 #ifdef FDB_DEV_ONLY_KP                                     // development builds: one row width only
         FDB_SWEEP_CASE(FDB_DEV_ONLY_KP)
@@ -558,6 +571,21 @@ extern "C" __attribute__((visibility("default"))) int fdb_bcd_sweep(const float 
     return dispatch_sweep(h, host_gram, n_types, beta_in, beta_out, indptr, indices, n_rows, lambda, rho_scaled,
                           tol, finalize, (SolveState *)state, plan, (cudaStream_t)stream);
 }
+
+namespace fdb {
+// used by peer.cu: one sweep with the boundary push and the inter-rank hand-shake fused in (production kernel only)
+bool sweep_can_fuse_comm(const float *host_gram, int n_types, float lam, const void *plan)
+{
+    return plan != nullptr && sweep_variant() == 0 && fdb_padded_types(n_types) % 8 == 0 && weak_coupling(host_gram, n_types, lam);
+}
+int sweep_with_comm(const float *h, const float *host_gram, const float *beta_in, float *beta_out, const int32_t *indptr,
+                    const int32_t *indices, int64_t n_rows, int32_t n_types, float lam, float rho, float tol, void *state,
+                    const void *plan, void *stream, const SweepComm &comm)
+{
+    return dispatch_sweep(h, host_gram, n_types, beta_in, beta_out, indptr, indices, n_rows, lam, rho, tol, 1,
+                          (SolveState *)state, plan, (cudaStream_t)stream, &comm);
+}
+}  // namespace fdb
 
 extern "C" __attribute__((visibility("default"))) int fdb_bcd_finalize(void *state, float tol, void *stream)
 {

@@ -167,6 +167,25 @@ __device__ __forceinline__ u64 sub2q(const u64 a, const u64 b)
 }
 
 
+// Multi-GPU extension of the production sweep kernel (world <= 1: unused).  The rank's boundary rows -- own rows that a
+// neighbouring tile reads as halo -- are written straight into the peers' beta_out buffers (NVLink peer memory) from
+// the store phase of the patch that produced them; patches holding boundary rows are walked FIRST (patch_order), so the
+// transfers overlap the interior patches.  The last CTA to finish then publishes the rank's two max-norm words and a
+// sweep sequence number into every peer's comm block, waits for theirs, reduces (MAX, core/solver.py:395-397) and runs
+// the stop test: one launch per sweep, no NCCL, no host synchronisation.  (Ordering argument: peer.cu.)
+constexpr int kMaxRanks = 16;
+struct SweepComm {
+    const int32_t *patch_order;     // [n_patches] processing order, boundary patches first (null: natural order)
+    const int32_t *n_boundary;      // device scalar: how many leading patches of that order hold boundary rows
+    const int32_t *push_ptr;        // [n_rows + 1] push entries of every own row
+    const int2 *push_ent;           // (peer, destination row inside the peer's beta buffers)
+    float *peer_base[kMaxRanks];    // symmetric buffers: [beta_a cap_rows*Kp][beta_b cap_rows*Kp][comm words]
+    long long out_off;              // float offset of beta_out inside a symmetric buffer
+    long long comm_off;             // float offset of the comm block
+    int rank, world;
+    unsigned seq;                   // sequence number of this sweep
+};
+
 inline PlanView plan_view(const void *plan, int64_t n_ctas, int tile)
 {
     const char *pbase = (const char *)plan;

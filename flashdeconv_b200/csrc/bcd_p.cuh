@@ -37,7 +37,7 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
                    const float *__restrict__ beta_in, float *__restrict__ beta_out,
                    const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices, PlanView plan,
                    int n_rows, int n_types, float lam, float rho, float tol, int finalize, SolveState *state,
-                   int n_patches)
+                   int n_patches, const __grid_constant__ SweepComm comm)
 {
     static_assert(KP % 8 == 0, "half gather rows need Kp % 8 == 0");
     using L = TileLayout<KP>;
@@ -51,8 +51,12 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
     uint8_t *idx_tile = reinterpret_cast<uint8_t *>(g_tile + (TILE + HCAP) * GROW);     // NW x kCodeRounds x 32 byte codes
     int *scal = reinterpret_cast<int *>(idx_tile + NW * kCodeRounds * 32);        // 3 x TILE: row start, end, halo id
     __shared__ unsigned red[2][NW];
+    __shared__ int s_last;
 
-    if (*reinterpret_cast<volatile int *>(&state->converged)) return;      // uniform across the grid
+    if (*reinterpret_cast<volatile int *>(&state->converged)) return;      // uniform across the grid (and across ranks)
+    const bool comm_on = comm.world > 1;
+    const int n_push_patches = comm_on ? __ldg(comm.n_boundary) : 0;
+    auto patch_at = [&](int pi) { return comm.patch_order ? __ldg(comm.patch_order + pi) : pi; };
 
     // Range of the fp16 gather tile.  Every |beta_in| is at most last_max_abs + last_max_diff (max|beta| of the sweep
     // before plus the largest step it took; fdb_bcd_init seeds 1/K), so with 2^x <= bound < 2^(x+1) the tile stores
@@ -100,16 +104,17 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
     };
 
     // ---------------- prologue: the first patch's scalars
-    int patch = blockIdx.x;
-    scalars_async(patch);
+    int pi = blockIdx.x;                                  // position in the processing order
+    int patch = pi < n_patches ? patch_at(pi) : n_patches;
+    if (patch < n_patches) scalars_async(patch);
     asm volatile("cp.async.commit_group;");
     asm volatile("cp.async.wait_all;");
 
     float dmax = 0.f, amax = 0.f;
 #pragma unroll 1
-    for (; patch < n_patches; patch += gridDim.x) {
+    for (; pi < n_patches; pi += gridDim.x) {
         const int tile_base = patch * TILE;
-        const int next = patch + gridDim.x;
+        const int next = pi + (int)gridDim.x < n_patches ? patch_at(pi + gridDim.x) : n_patches;
         const int my_row = tile_base + own;
         const int my_s = scal[threadIdx.x], my_e = scal[TILE + threadIdx.x];
         const int halo_id = scal[2 * TILE + threadIdx.x];
@@ -310,7 +315,20 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
             const int p = tile_base + wrow + lr;
             if (p < n_rows) st4(beta_out + (size_t)p * KP + 4 * q, ld4(c_tile + L::at(wrow + lr, q)));
         }
+        // ---------------- boundary rows -> the neighbouring tiles' halo slots (peer memory), from registers
+        if (pi < n_push_patches && my_row < n_rows) {
+            const int pe = __ldg(comm.push_ptr + my_row + 1);
+            for (int u = __ldg(comm.push_ptr + my_row); u < pe; ++u) {
+                const int2 ent = __ldg(comm.push_ent + u);
+                float *dst = comm.peer_base[ent.x] + comm.out_off + (long long)ent.y * KP;
+#pragma unroll
+                for (int q = 0; q < Q; ++q)
+                    st4(dst + 4 * q, make_float4(b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]));
+            }
+        }
+        patch = next;
     }
+    if (comm_on) __threadfence_system();                  // this thread's peer writes before the CTA's arrival below
 
     const unsigned wd = __reduce_max_sync(kFull, __float_as_uint(dmax));
     const unsigned wa = __reduce_max_sync(kFull, __float_as_uint(amax));
@@ -322,13 +340,57 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
         for (int w = 0; w < NW; ++w) { bd = max(bd, red[0][w]); ba = max(ba, red[1][w]); }
         if (bd > *reinterpret_cast<volatile unsigned *>(&state->max_diff_bits)) atomicMax(&state->max_diff_bits, bd);
         if (ba > *reinterpret_cast<volatile unsigned *>(&state->max_abs_bits)) atomicMax(&state->max_abs_bits, ba);
+        s_last = 0;
         if (finalize) {
-            __threadfence();
+            if (comm_on) __threadfence_system(); else __threadfence();
             if (atomicAdd(&state->arrived, 1u) == gridDim.x - 1) {
                 __threadfence();
-                finalize_state(state, tol);
+                if (comm_on) s_last = 1;
+                else finalize_state(state, tol);
             }
         }
+    }
+    if (!(finalize && comm_on)) return;
+    // ---------------- multi-GPU: the last CTA exchanges max norms + sequence flags with every peer, then finalises
+    __syncthreads();
+    if (!s_last) return;
+    __shared__ int s_timeout;
+    if (threadIdx.x == 0) s_timeout = 0;
+    __syncthreads();
+    const int parity = (int)(comm.seq & 1u);
+    if ((int)threadIdx.x < comm.world) {
+        const int peer = threadIdx.x;
+        unsigned *pc = reinterpret_cast<unsigned *>(comm.peer_base[peer] + comm.comm_off);       // the peer's comm block
+        unsigned *slot = pc + kMaxRanks + (parity * kMaxRanks + comm.rank) * 2;
+        __threadfence_system();                      // after every CTA's sweep + pushes (observed through `arrived`)
+        slot[0] = *reinterpret_cast<volatile unsigned *>(&state->max_diff_bits);
+        slot[1] = *reinterpret_cast<volatile unsigned *>(&state->max_abs_bits);
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pc + comm.rank), "r"(comm.seq) : "memory");
+        const unsigned *mine = reinterpret_cast<const unsigned *>(comm.peer_base[comm.rank] + comm.comm_off);
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + peer) : "memory");
+            if ((int)(v - comm.seq) >= 0) break;
+            if (clock64() - t0 > 120000000000LL) { s_timeout = 1; break; }                       // ~60 s: a peer is gone
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (s_timeout) { state->converged = 2; state->arrived = 0u; return; }                    // surfaced as an error by the host
+        const unsigned *mine = reinterpret_cast<const unsigned *>(comm.peer_base[comm.rank] + comm.comm_off);
+        unsigned md = 0u, ma = 0u;
+        for (int p = 0; p < comm.world; ++p) {
+            unsigned a, c;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(a) : "l"(mine + kMaxRanks + (parity * kMaxRanks + p) * 2) : "memory");
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(c) : "l"(mine + kMaxRanks + (parity * kMaxRanks + p) * 2 + 1) : "memory");
+            md = max(md, a);
+            ma = max(ma, c);
+        }
+        state->max_diff_bits = md;
+        state->max_abs_bits = ma;
+        finalize_state(state, tol);
     }
 }
 
@@ -337,7 +399,7 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
 template <int KP>
 int launch_sweep_p(const float *h, const GramArg<KP> &G, int n_types, const float *beta_in, float *beta_out,
                    const int32_t *indptr, const int32_t *indices, int64_t n_rows, float lam, float rho, float tol,
-                   int finalize, SolveState *state, const void *plan, cudaStream_t st)
+                   int finalize, SolveState *state, const void *plan, cudaStream_t st, const SweepComm *comm)
 {
     // 128-spot patches (4 warps); residency by row width (shared memory): 6 CTAs/SM at 36 KB (Kp <= 32), 4 at 46-54 KB
     // (Kp = 40, 48), 3 at 62-68 KB (Kp = 56, 64)
@@ -356,6 +418,14 @@ int launch_sweep_p(const float *h, const GramArg<KP> &G, int n_types, const floa
     }
     const size_t smem = (size_t)tile * TileLayout<KP>::S * 4 + (size_t)2 * tile * (KP / 2) * 4 +
                         (size_t)NWH * kCodeRounds * 32 + (size_t)3 * tile * 4;
+    SweepComm cm;
+    if (comm) cm = *comm;
+    else {
+        cm = SweepComm();
+        cm.patch_order = nullptr; cm.n_boundary = nullptr; cm.push_ptr = nullptr; cm.push_ent = nullptr;
+        for (int p = 0; p < kMaxRanks; ++p) cm.peer_base[p] = nullptr;
+        cm.out_off = cm.comm_off = 0; cm.rank = 0; cm.world = 1; cm.seq = 0u;
+    }
     auto run_p = [&](auto kern) -> int {
         int resident = 0;
         FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -364,7 +434,7 @@ int launch_sweep_p(const float *h, const GramArg<KP> &G, int n_types, const floa
         static const int cap = getenv("FDB_SWEEP_MAX_CTAS") ? std::max(atoi(getenv("FDB_SWEEP_MAX_CTAS")), 1) : 1 << 30;
         const int grid = (int)std::min<int64_t>(std::min<int64_t>(n_ctas, cap), (int64_t)kNumSM * std::max(resident, 1));
         kern<<<grid, tile, smem, st>>>(h, P, beta_in, beta_out, indptr, indices, pv, (int)n_rows, n_types, lam, rho, tol,
-                                       finalize, state, (int)n_ctas);
+                                       finalize, state, (int)n_ctas, cm);
         FDB_LAUNCH_CHECK("bcd_sweep_p_kernel");
         return FDB_OK;
     };

@@ -6,5 +6,5 @@
 namespace fdb {
 template int launch_sweep_p<FDB_P_KP>(const float *, const GramArg<FDB_P_KP> &, int, const float *, float *, const int32_t *,
                                       const int32_t *, int64_t, float, float, float, int, SolveState *, const void *,
-                                      cudaStream_t);
+                                      cudaStream_t, const SweepComm *);
 }

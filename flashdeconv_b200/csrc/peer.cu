@@ -2,14 +2,16 @@
 //
 // Every rank's beta buffers live in a symmetric allocation that all peers have mapped (the host layer
 // obtains the mapping, e.g. torch symmetric memory / CUDA IPC, and passes the peers' base pointers).
-// Per sweep, on ONE stream and without host synchronisation:
-//   1. fdb_bcd_sweep on the rank's own rows (finalize = 0);
-//   2. peer_push_kernel: the boundary rows each neighbour needs are written STRAIGHT into that
-//      neighbour's halo slots over NVLink (128-byte rows, coalesced 16-byte stores);
-//   3. peer_sync_kernel: one thread per rank publishes this rank's two max-norm words and a sweep sequence
-//      number into every peer's comm block (fence.sys + release store), spins until every peer's
-//      sequence number has arrived here (acquire loads), then reduces the max norms and runs the stop
-//      test -- the MAX all-reduce of core/solver.py:395-397 and the halo hand-shake in one 1-block kernel.
+// Per sweep, on ONE stream and without host synchronisation, ONE launch (bcd_p.cuh, SweepComm):
+//   1. the sweep kernel walks the patches that hold boundary rows first and writes those rows STRAIGHT into the
+//      neighbours' halo slots over NVLink from its store phase (128-byte rows, 16-byte stores), overlapping the
+//      interior patches;
+//   2. its last CTA publishes this rank's two max-norm words and a sweep sequence number into every peer's comm
+//      block (fence.sys + release store), spins until every peer's sequence number has arrived here (acquire
+//      loads), then reduces the max norms and runs the stop test -- the MAX all-reduce of core/solver.py:395-397
+//      and the halo hand-shake.
+// (With the fp32-gather fallback kernel the same three steps run as three launches: sweep, peer_push_kernel,
+// peer_sync_kernel.)
 // Ordering argument (two beta buffers X, Y alternate): a rank starts sweep t+1 only after every peer's
 // flag t, which a peer writes after its sweep t and push t completed; so rows pushed for sweep t+1 can never
 // overwrite halo rows a peer is still reading in sweep t, and the rows read in sweep t+2 were pushed
@@ -17,7 +19,7 @@
 //
 // Symmetric buffer layout (floats): [beta_a: cap_rows*Kp][beta_b: cap_rows*Kp][comm: kCommWords u32]
 //   comm: flags[kMaxRanks], stats[2][kMaxRanks][2]
-#include "bcd_state.cuh"
+#include "bcd_common.cuh"
 
 extern "C" int fdb_bcd_sweep(const float *h, const float *host_gram, const float *beta_in, float *beta_out,
                              const int32_t *indptr, const int32_t *indices, int64_t n_rows, int32_t n_types,
@@ -27,24 +29,33 @@ extern "C" int fdb_bcd_init(float *beta, int64_t n_rows, int32_t n_types, void *
 
 namespace fdb {
 
-constexpr int kMaxRanks = 16;
+bool sweep_can_fuse_comm(const float *host_gram, int n_types, float lam, const void *plan);
+int sweep_with_comm(const float *h, const float *host_gram, const float *beta_in, float *beta_out, const int32_t *indptr,
+                    const int32_t *indices, int64_t n_rows, int32_t n_types, float lam, float rho, float tol, void *state,
+                    const void *plan, void *stream, const SweepComm &comm);
+
 constexpr int kCommWords = kMaxRanks + 2 * kMaxRanks * 2;      // 80 words; the host reserves 256
 
 struct PeerBases {
     float *base[kMaxRanks];
 };
 
+// unfused fallback (fp32-gather sweep kernel): one thread per (own row, 16-byte chunk); rows without entries cost a load
 __global__ void __launch_bounds__(256)
-peer_push_kernel(const float *__restrict__ beta_local, PeerBases pb, int64_t buf_off, const int32_t *__restrict__ src_row,
-                 const int32_t *__restrict__ dst_peer, const int64_t *__restrict__ dst_row, int64_t n_push, int chunks)
+peer_push_kernel(const float *__restrict__ beta_local, PeerBases pb, int64_t buf_off, const int32_t *__restrict__ push_ptr,
+                 const int2 *__restrict__ push_ent, int64_t n_own, int chunks, const SolveState *st)
 {
+    if (st->converged) return;
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_push * chunks) return;
-    const int64_t e = t / chunks;
-    const int q = (int)(t - e * chunks);
-    const float4 v = *reinterpret_cast<const float4 *>(beta_local + ((int64_t)src_row[e] * chunks + q) * 4);
-    float *dst = pb.base[dst_peer[e]] + buf_off + (dst_row[e] * chunks + q) * 4;
-    *reinterpret_cast<float4 *>(dst) = v;
+    if (t >= n_own * chunks) return;
+    const int64_t row = t / chunks;
+    const int q = (int)(t - row * chunks);
+    const int pe = push_ptr[row + 1];
+    for (int u = push_ptr[row]; u < pe; ++u) {
+        const int2 ent = push_ent[u];
+        const float4 v = *reinterpret_cast<const float4 *>(beta_local + (row * chunks + q) * 4);
+        *reinterpret_cast<float4 *>(pb.base[ent.x] + buf_off + ((int64_t)ent.y * chunks + q) * 4) = v;
+    }
 }
 
 __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v)
@@ -58,6 +69,7 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
     return v;
 }
 
+// start-of-solve rendezvous (do_finalize = 0) and the hand-shake of the unfused fallback loop
 __global__ void __launch_bounds__(kMaxRanks)
 peer_sync_kernel(SolveState *st, PeerBases pb, int64_t comm_off, int rank, int world, unsigned seq, float tol,
                  int do_finalize)
@@ -79,7 +91,7 @@ peer_sync_kernel(SolveState *st, PeerBases pb, int64_t comm_off, int rank, int w
         const unsigned *mine = reinterpret_cast<const unsigned *>(pb.base[rank] + comm_off);
         const long long t0 = clock64();
         while ((int)(ld_acquire_sys(mine + peer) - seq) < 0) {
-            if (clock64() - t0 > 20000000000LL) { timed_out = 1; break; }            // ~10 s: a peer is gone
+            if (clock64() - t0 > 120000000000LL) { timed_out = 1; break; }           // ~60 s: a peer is gone
         }
     }
     __syncthreads();
@@ -109,14 +121,15 @@ FDB_API int64_t fdb_peer_comm_floats(void) { return 256; }
 FDB_API int fdb_bcd_solve_peer(const float *h, const float *host_gram, void *const *host_peer_base, int32_t rank,
                                int32_t world, int64_t cap_rows, const int32_t *indptr, const int32_t *indices,
                                int64_t n_own, int64_t n_total, int32_t n_types, float lambda, float rho_scaled,
-                               int32_t max_iter, float tol, void *state, int64_t n_push, const int32_t *push_src_row,
-                               const int32_t *push_peer, const int64_t *push_dst_row, uint32_t seq_base,
+                               int32_t max_iter, float tol, void *state, const int32_t *push_ptr, const void *push_ent,
+                               const int32_t *patch_order, const int32_t *n_boundary, uint32_t seq_base,
                                const void *plan, void *stream)
 {
     FDB_REQUIRE(host_peer_base && state, "null peer table / state");
     FDB_REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world, "world must be in [1, %d]", kMaxRanks);
     FDB_REQUIRE(n_own >= 0 && n_total >= n_own && n_total <= cap_rows && max_iter >= 0, "bad sizes");
     FDB_REQUIRE(n_types >= 1 && n_types <= FDB_MAX_TYPES, "n_types must be in [1, %d], got %d", FDB_MAX_TYPES, n_types);
+    FDB_REQUIRE(world == 1 || (push_ptr && push_ent), "null push lists");
     cudaStream_t st = (cudaStream_t)stream;
     const int kp = fdb_padded_types(n_types);
     PeerBases pb;
@@ -131,22 +144,41 @@ FDB_API int fdb_bcd_solve_peer(const float *h, const float *host_gram, void *con
     // reading the previous solve's result (those kernels precede this one in stream order)
     peer_sync_kernel<<<1, kMaxRanks, 0, st>>>((SolveState *)state, pb, off_comm, rank, world, seq_base, tol, 0);
     FDB_LAUNCH_CHECK("peer_sync_kernel");
+    // one launch per sweep when the production sweep kernel runs (push + hand-shake fused in); otherwise three
+    const bool fused = n_own > 0 && world > 1 && sweep_can_fuse_comm(host_gram, n_types, lambda, plan);
+    SweepComm cm;
+    cm.patch_order = patch_order;
+    cm.n_boundary = n_boundary;
+    cm.push_ptr = push_ptr;
+    cm.push_ent = (const int2 *)push_ent;
+    for (int p = 0; p < kMaxRanks; ++p) cm.peer_base[p] = pb.base[p];
+    cm.comm_off = off_comm;
+    cm.rank = rank;
+    cm.world = world;
     int64_t cur = off_a, nxt = off_b;
     const int chunks = kp / 4;
     for (int it = 0; it < max_iter; ++it) {
-        if (n_own > 0) {
-            rc = fdb_bcd_sweep(h, host_gram, mine + cur, mine + nxt, indptr, indices, n_own, n_types, lambda, rho_scaled,
-                               tol, 0, state, plan, stream);
+        const unsigned seq = seq_base + (unsigned)it + 1u;
+        if (fused && n_boundary != nullptr) {
+            cm.out_off = nxt;
+            cm.seq = seq;
+            rc = sweep_with_comm(h, host_gram, mine + cur, mine + nxt, indptr, indices, n_own, n_types, lambda, rho_scaled,
+                                 tol, state, plan, stream, cm);
             if (rc) return rc;
+        } else {
+            if (n_own > 0) {
+                rc = fdb_bcd_sweep(h, host_gram, mine + cur, mine + nxt, indptr, indices, n_own, n_types, lambda,
+                                   rho_scaled, tol, 0, state, plan, stream);
+                if (rc) return rc;
+                if (world > 1) {
+                    peer_push_kernel<<<(int)ceil_div(n_own * chunks, 256), 256, 0, st>>>(
+                        mine + nxt, pb, nxt, push_ptr, (const int2 *)push_ent, n_own, chunks, (const SolveState *)state);
+                    FDB_LAUNCH_CHECK("peer_push_kernel");
+                }
+            }
+            peer_sync_kernel<<<1, kMaxRanks, 0, st>>>((SolveState *)state, pb, off_comm, rank, world, seq, tol, 1);
+            FDB_LAUNCH_CHECK("peer_sync_kernel");
         }
-        if (n_push > 0) {
-            peer_push_kernel<<<(int)ceil_div(n_push * chunks, 256), 256, 0, st>>>(mine + nxt, pb, nxt, push_src_row,
-                                                                                  push_peer, push_dst_row, n_push, chunks);
-            FDB_LAUNCH_CHECK("peer_push_kernel");
-        }
-        peer_sync_kernel<<<1, kMaxRanks, 0, st>>>((SolveState *)state, pb, off_comm, rank, world,
-                                                  seq_base + (unsigned)it + 1u, tol, 1);
-        FDB_LAUNCH_CHECK("peer_sync_kernel");
         const int64_t t = cur; cur = nxt; nxt = t;
     }
     return FDB_OK;

@@ -114,6 +114,109 @@ def plan_tile(indptr, indices, bounds: List[Tuple[int, int]], rank: int) -> Tile
                     local.to(torch.int32).contiguous(), halo_global, recv, send)
 
 
+@dataclass
+class DeviceTilePlan:
+    """What `plan_tile` computes, built on the device with ONE small device->host read (the R x R boundary-count
+    matrix and two row pointers), plus what the fused sweep kernel wants: the boundary rows as a per-row list of
+    (peer, destination row) and a patch order with the boundary patches first."""
+    rank: int
+    lo: int
+    hi: int
+    n_own: int
+    n_halo: int
+    cap_rows: int                  # max over ranks of own + halo rows (size of the symmetric beta buffers)
+    indptr: "object"               # int32[n_own + 1]
+    indices: "object"              # int32[nnz_local], local numbering
+    halo_global: "object"          # int64[n_halo]
+    push_ptr: "object"             # int32[n_own + 1]
+    push_ent: "object"             # int32[T, 2]  (peer, destination row in the peer's buffers)
+    patch_order: "object"          # int32[n_patches]
+    n_boundary: "object"           # int32[1] (device)
+    recv: List[Tuple[int, int, int]]
+
+    @property
+    def n_total(self) -> int:
+        return self.n_own + self.n_halo
+
+
+def plan_tile_device(indptr, indices, nnz: int, bounds: List[Tuple[int, int]], rank: int, patch: int = 128) -> DeviceTilePlan:
+    """Same partition as `plan_tile`, from the replicated global CSR (tile order) on the device.  Every rank computes the
+    whole R x R matrix of boundary-row counts from its own copy of the graph, so no collective is needed."""
+    import torch
+    t = torch
+    dev = indptr.device
+    n = int(indptr.numel()) - 1
+    R = len(bounds)
+    lo, hi = bounds[rank]
+    n_own = hi - lo
+    i32, i64 = t.int32, t.int64
+    starts = t.tensor([b[0] for b in bounds] + [n], device=dev, dtype=i64)
+    ptr = indptr.to(i64)
+    idx = indices[:nnz].to(i64)
+    pos = t.arange(n, device=dev, dtype=i64)
+    owner = t.bucketize(pos, starts[1:], right=True)                    # owner rank of every position
+    edge_row = t.repeat_interleave(pos, ptr[1:] - ptr[:-1], output_size=nnz)
+    dst_owner = owner[idx]
+    cross = owner[edge_row] != dst_owner
+    flags = t.zeros(n * R + 1, device=dev, dtype=i32)
+    flags.scatter_(0, t.where(cross, edge_row * R + dst_owner, t.full_like(idx, n * R)),
+                   t.ones(1, device=dev, dtype=i32).expand(nnz))
+    flags = flags[: n * R].view(n, R)                                   # flags[i, q] = row i has a neighbour owned by q
+    counts_dev = t.stack([flags[a:b].sum(0, dtype=i64) for a, b in bounds])          # counts[r, q]
+    head = t.cat([counts_dev.flatten(), ptr[lo:lo + 1], ptr[hi:hi + 1]]).cpu().tolist()     # the one host read
+    counts = [head[r * R:(r + 1) * R] for r in range(R)]
+    e0, e1 = int(head[-2]), int(head[-1])
+    n_halo_of = [sum(counts[r][q] for r in range(R)) for q in range(R)]
+    n_halo = n_halo_of[rank]
+    cap_rows = max(max((b[1] - b[0]) + n_halo_of[q] for q, b in enumerate(bounds)), 1)
+    recv, first = [], 0
+    for r in range(R):
+        if r != rank and counts[r][rank] > 0:
+            recv.append((r, first, counts[r][rank]))
+        first += counts[r][rank]
+    # where my boundary rows live in each peer's buffers: after its own rows, behind the rows of lower ranks
+    base = t.tensor([(bounds[q][1] - bounds[q][0]) + sum(counts[r][q] for r in range(rank)) for q in range(R)],
+                    device=dev, dtype=i64)
+    my = flags[lo:hi].to(i64)                                           # n_own x R
+    qrank = t.cumsum(my, 0) - my
+    push_cnt = my.sum(1)
+    push_ptr = t.zeros(n_own + 1, device=dev, dtype=i64)
+    t.cumsum(push_cnt, 0, out=push_ptr[1:])
+    within = t.cumsum(my, 1) - my
+    T = sum(counts[rank])
+    tgt = t.where(my > 0, push_ptr[:-1, None] + within, t.full_like(my, T)).flatten()
+    ent = t.zeros((T + 1, 2), device=dev, dtype=i32)
+    peers = t.arange(R, device=dev, dtype=i32).expand(n_own, R).reshape(-1)
+    ent[:, 0].scatter_(0, tgt, peers)
+    ent[:, 1].scatter_(0, tgt, (base[None, :] + qrank).to(i32).flatten())
+    # halo rows: the outside neighbours of my rows, ascending global position (= grouped by owner)
+    nbr = idx[e0:e1]
+    outside = (nbr < lo) | (nbr >= hi)
+    hflag = t.zeros(n + 1, device=dev, dtype=i64)
+    hflag.scatter_(0, t.where(outside, nbr, t.full_like(nbr, n)), t.ones(1, device=dev, dtype=i64).expand(nbr.numel()))
+    hflag = hflag[:n]
+    hscan = t.cumsum(hflag, 0) - hflag
+    local = t.where(outside, n_own + hscan[nbr], nbr - lo).to(i32)
+    halo_global = t.zeros(n_halo + 1, device=dev, dtype=i64)
+    halo_global.scatter_(0, t.where(hflag > 0, hscan, t.full_like(hscan, n_halo)), pos)
+    # patches holding boundary rows first
+    n_patches = max(-(-n_own // patch), 1)
+    padded = t.zeros(n_patches * patch, device=dev, dtype=i64)
+    padded[:n_own] = push_cnt
+    bflag = (padded.view(n_patches, patch).sum(1) > 0).to(i64)
+    brank = t.cumsum(bflag, 0) - bflag
+    n_boundary = bflag.sum()
+    pid = t.arange(n_patches, device=dev, dtype=i64)
+    position = t.where(bflag > 0, brank, n_boundary + (pid - brank))
+    order = t.empty(n_patches, device=dev, dtype=i32)
+    order.scatter_(0, position, pid.to(i32))
+    if local.numel() == 0:
+        local = t.zeros(1, dtype=i32, device=dev)
+    return DeviceTilePlan(rank, lo, hi, n_own, n_halo, cap_rows, (ptr[lo:hi + 1] - e0).to(i32).contiguous(),
+                          local.contiguous(), halo_global[:n_halo], push_ptr.to(i32).contiguous(),
+                          ent[: max(T, 1)].contiguous(), order, n_boundary.to(i32).reshape(1), recv)
+
+
 def halo_exchange(beta, plan: TilePlan, pack: Callable, group=None, tag: int = 0):
     """Fill the halo rows of `beta` (n_total x row_floats) with the owners' current rows.
 
@@ -155,8 +258,9 @@ class TiledPath:
         self.dev = csr.indices.device
         self.gene_bucket = torch.from_numpy(tables.gene_bucket).to(self.dev)
         self.gene_weight = torch.from_numpy(tables.gene_weight).to(self.dev)
-        xst = np.zeros((tables.d, self.Kp), dtype=np.float32)
-        xst[:, : self.K] = tables.X_sketch.T
+        self.d_dev = 4 * ((tables.d + 3) // 4)                     # see pipeline.DevicePath
+        xst = np.zeros((self.d_dev, self.Kp), dtype=np.float32)
+        xst[: tables.d, : self.K] = tables.X_sketch.T
         self.x_sketch_t = torch.from_numpy(xst).to(self.dev)
         self.gram32 = np.ascontiguousarray(tables.gram, dtype=np.float32)
         self.state = torch.zeros(16, dtype=torch.int32, device=self.dev)
@@ -207,38 +311,37 @@ class TiledPath:
         self.graph = pl.build_graph(self.coords, method, k, radius)       # replicated, deterministic
         n = int(self.graph.order.numel())
         self.bounds = tile_bounds(n, self.world)
-        self.plan = plan_tile(self.graph.indptr, self.graph.indices[: max(self.graph.nnz, 1)], self.bounds, self.rank)
+        if self.mode == "peer":
+            self.plan = plan_tile_device(self.graph.indptr, self.graph.indices, self.graph.nnz, self.bounds, self.rank)
+        else:
+            self.plan = plan_tile(self.graph.indptr, self.graph.indices[: max(self.graph.nnz, 1)], self.bounds, self.rank)
         p = self.plan
         if p.indices.numel() == 0:
             p.indices = t.zeros(1, dtype=t.int32, device=self.dev)
         self.h = t.empty((max(p.n_own, 1), self.Kp), dtype=t.float32, device=self.dev)
         self.ysq = t.empty(max(p.n_own, 1), dtype=t.float32, device=self.dev)
-        self.beta_a = t.empty((max(p.n_total, 1), self.Kp), dtype=t.float32, device=self.dev)
-        self.beta_b = t.empty((max(p.n_total, 1), self.Kp), dtype=t.float32, device=self.dev)
-        self.send_bufs = [t.empty((rows.numel(), self.Kp), dtype=t.float32, device=self.dev) for _, rows in p.send]
         if self.mode == "peer":
             try:
                 self._setup_peer()
+                return self.graph
             except Exception as exc:          # no P2P mapping on this box: fall back to the NCCL loop
                 import warnings
                 warnings.warn(f"peer-memory halo exchange unavailable ({exc!r}); using NCCL send/recv")
                 self.mode = "nccl"
+                self.plan = p = plan_tile(self.graph.indptr, self.graph.indices[: max(self.graph.nnz, 1)], self.bounds,
+                                          self.rank)
                 if self.comm is None:
                     self.comm = self._native_comm()
+        self.beta_a = t.empty((max(p.n_total, 1), self.Kp), dtype=t.float32, device=self.dev)
+        self.beta_b = t.empty((max(p.n_total, 1), self.Kp), dtype=t.float32, device=self.dev)
+        self.send_bufs = [t.empty((rows.numel(), self.Kp), dtype=t.float32, device=self.dev) for _, rows in p.send]
         return self.graph
 
     def _setup_peer(self):
-        """Symmetric beta buffers (mapped by every peer) + the push list for direct NVLink halo writes."""
+        """Symmetric beta buffers (mapped by every peer), cached per (size, group)."""
         import torch.distributed._symmetric_memory as symm_mem
         t, p, dist = self.torch, self.plan, self.dist
-        # one small all-gather: every rank's (n_own, n_total, first halo slot reserved for each peer)
-        mine = [p.n_own, p.n_total] + [-1] * self.world
-        for peer, first, _ in p.recv:
-            mine[2 + peer] = first
-        table = t.empty((self.world, self.world + 2), dtype=t.int64, device=self.dev)
-        dist.all_gather_into_tensor(table, t.tensor(mine, dtype=t.int64, device=self.dev), group=self.group)
-        meta = table.cpu().tolist()
-        cap_rows = max(max(row[1] for row in meta), 1)
+        cap_rows = p.cap_rows
         comm_floats = int(self.lib.fdb_peer_comm_floats())
         total = 2 * cap_rows * self.Kp + comm_floats
         key = (total, id(self.group))
@@ -254,16 +357,6 @@ class TiledPath:
         self.cap_rows = cap_rows
         self.beta_a = self.symm_buf[: cap_rows * self.Kp].view(cap_rows, self.Kp)
         self.beta_b = self.symm_buf[cap_rows * self.Kp: 2 * cap_rows * self.Kp].view(cap_rows, self.Kp)
-        # where do my boundary rows live in each neighbour's buffer?  (its n_own + the first slot of my slice there)
-        src, peers, dst = [], [], []
-        for peer, rows in p.send:
-            base = meta[peer][0] + meta[peer][2 + self.rank]
-            src.append(rows.to(t.int32))
-            peers.append(t.full((rows.numel(),), peer, dtype=t.int32, device=self.dev))
-            dst.append(base + t.arange(rows.numel(), dtype=t.int64, device=self.dev))
-        cat = lambda xs, dt: (t.cat(xs) if xs else t.zeros(1, dtype=dt, device=self.dev)).contiguous()
-        self.n_push = int(sum(r.numel() for _, r in p.send))
-        self.push_src, self.push_peer, self.push_dst = cat(src, t.int32), cat(peers, t.int32), cat(dst, t.int64)
 
     def stage_sketch(self):
         c, tb, p = self.csr, self.tables, self.plan
@@ -271,10 +364,11 @@ class TiledPath:
             return
         row_ids = self.graph.order[p.lo:p.hi].contiguous()
         self._row_ids = row_ids
-        self.check(self.lib.fdb_sketch_contract_csr(
+        fn = self.lib.fdb_sketch_linear_contract_csr if tb.linear else self.lib.fdb_sketch_contract_csr
+        self.check(fn(
             self.pl._ptr(c.indptr), int(c.indptr.dtype == self.torch.int64), self.pl._ptr(c.indices),
             self.pl._ptr(c.data), p.n_own, c.shape[1], self.pl._ptr(self.gene_bucket), self.pl._ptr(self.gene_weight),
-            tb.d, self.pl._ptr(self.x_sketch_t), self.K, self.pl._ptr(None), self.pl._ptr(row_ids), int(len(tb.bucket)),
+            self.d_dev, self.pl._ptr(self.x_sketch_t), self.K, self.pl._ptr(None), self.pl._ptr(row_ids), int(len(tb.bucket)),
             self.pl._ptr(self.h), self.pl._ptr(self.ysq), self._stream()), "sketch_contract_csr")
 
     def lambda_auto(self, alpha=0.005) -> float:
@@ -315,7 +409,7 @@ class TiledPath:
             self.check(self.lib.fdb_bcd_solve_peer(
                 pl._ptr(self.h), gram, bases, self.rank, self.world, self.cap_rows, pl._ptr(p.indptr), pl._ptr(p.indices),
                 p.n_own, p.n_total, self.K, float(lam), float(rho_scaled), int(max_iter), float(tol), pl._ptr(self.state),
-                self.n_push, pl._ptr(self.push_src), pl._ptr(self.push_peer), pl._ptr(self.push_dst), seq,
+                pl._ptr(p.push_ptr), pl._ptr(p.push_ent), pl._ptr(p.patch_order), pl._ptr(p.n_boundary), seq,
                 pl._ptr(self.sweep_plan), st),
                 "bcd_solve_peer")
             return

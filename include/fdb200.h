@@ -225,17 +225,21 @@ int fdb_bcd_solve_tiled(const float *h, const float *host_gram, float *beta_a, f
 /* Peer-memory form of fdb_bcd_solve_tiled: no NCCL on the data path.  Every rank's beta buffers live in a
  * symmetric allocation mapped by all peers; host_peer_base[p] is rank p's base pointer as seen from THIS
  * process.  Layout (floats): beta_a [cap_rows x Kp], beta_b [cap_rows x Kp], comm [fdb_peer_comm_floats()],
- * identical on all ranks (cap_rows >= every rank's n_total).  Per sweep: sweep own rows -> write the boundary
- * rows straight into the neighbours' halo slots over NVLink (push_src_row[e] of this rank's buffer goes to row
- * push_dst_row[e] of rank push_peer[e]'s buffer; device arrays) -> one 1-block kernel publishes the two
- * max-norm words + a sequence number to every peer, waits for all peers' and applies the stop test.
+ * identical on all ranks (cap_rows >= every rank's n_total).
+ * Boundary rows are described per own row (device arrays): entries push_ptr[i] .. push_ptr[i + 1] of push_ent, each
+ * an int32 pair (peer, row of the peer's buffers that receives own row i).  patch_order (int32, one entry per
+ * 128-row patch of the own rows, patches that hold boundary rows FIRST) and n_boundary (device int32: how many
+ * patches that is) let the sweep kernel write the boundary rows into the neighbours' halo slots from its own store
+ * phase, ahead of the interior patches; its last block then publishes the two max-norm words + a sequence number to
+ * every peer, waits for all peers' and applies the stop test: ONE launch per sweep.  patch_order / n_boundary may be
+ * NULL (natural order; push + hand-shake then run as separate launches, as they also do with the fp32 fallback sweep).
  * seq_base must grow by more than max_iter between successive solves on the same allocation. */
 int64_t fdb_peer_comm_floats(void);
 int fdb_bcd_solve_peer(const float *h, const float *host_gram, void *const *host_peer_base, int32_t rank,
                        int32_t world, int64_t cap_rows, const int32_t *indptr, const int32_t *indices,
                        int64_t n_own, int64_t n_total, int32_t n_types, float lambda, float rho_scaled,
-                       int32_t max_iter, float tol, void *state, int64_t n_push, const int32_t *push_src_row,
-                       const int32_t *push_peer, const int64_t *push_dst_row, uint32_t seq_base,
+                       int32_t max_iter, float tol, void *state, const int32_t *push_ptr, const void *push_ent,
+                       const int32_t *patch_order, const int32_t *n_boundary, uint32_t seq_base,
                        const void *plan, void *stream);
 
 /* Multi-GPU helpers: gather / scatter whole beta rows by index list (halo exchange staging). */

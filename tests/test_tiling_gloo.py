@@ -109,3 +109,41 @@ def test_two_rank_gloo_solve_matches_single_process(tmp_path):
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
     assert np.allclose(parts[0]["rels"], parts[1]["rels"])          # both ranks see the same global stop statistic
     assert all(p["n_send"] > 0 for p in parts)
+
+
+def test_device_plan_equals_reference_plan():
+    """plan_tile_device (sync-light, what the fused multi-GPU sweep consumes) against plan_tile on every rank: same
+    local adjacency and halo rows, and push lists that land each boundary row exactly where the peer's halo slice
+    expects it (its own rows, then the rows of lower ranks, ascending position)."""
+    from flashdeconv_b200 import tiling
+    for n, world, seed in ((900, 2, 3), (5000, 4, 5), (2300, 8, 7), (300, 3, 1)):
+        A, _, _ = _problem(n=n, seed=seed)
+        ptr = torch.from_numpy(A.indptr.astype(np.int32))
+        idx = torch.from_numpy(A.indices.astype(np.int32))
+        bounds = tiling.tile_bounds(n, world, align=128)
+        ref = [tiling.plan_tile(ptr, idx, bounds, r) for r in range(world)]
+        dev = [tiling.plan_tile_device(ptr, idx, int(idx.numel()), bounds, r) for r in range(world)]
+        for r in range(world):
+            a, b = ref[r], dev[r]
+            assert (a.n_own, a.n_halo) == (b.n_own, b.n_halo)
+            assert torch.equal(a.indptr, b.indptr) and torch.equal(a.indices[: int(a.indptr[-1])], b.indices[: int(b.indptr[-1])])
+            assert torch.equal(a.halo_global, b.halo_global)
+            assert sorted(a.recv) == sorted(b.recv)
+            assert b.cap_rows == max(x.n_total for x in ref)
+            # push entries grouped by peer must reproduce the reference send lists and land in the peer's recv slice
+            ent = b.push_ent[: int(b.push_ptr[-1])]
+            rows = torch.repeat_interleave(torch.arange(b.n_own), (b.push_ptr[1:] - b.push_ptr[:-1]).long())
+            for peer, send_rows in a.send:
+                sel = ent[:, 0] == peer
+                assert torch.equal(rows[sel].to(torch.int32), send_rows)
+                first = [f for (q, f, c) in ref[peer].recv if q == r][0]
+                want = ref[peer].n_own + first + torch.arange(int(sel.sum()))
+                assert torch.equal(ent[sel, 1].long(), want)
+            assert sum(len(sr) for _, sr in a.send) == int(b.push_ptr[-1])
+            # patch order: a permutation with the boundary patches first
+            nb = int(b.n_boundary)
+            order = b.patch_order.long()
+            assert sorted(order.tolist()) == list(range(order.numel()))
+            cnt = b.push_ptr[1:] - b.push_ptr[:-1]
+            has = [bool(cnt[q * 128:(q + 1) * 128].sum() > 0) for q in range(order.numel())]
+            assert all(has[q] for q in order[:nb].tolist()) and not any(has[q] for q in order[nb:].tolist())
