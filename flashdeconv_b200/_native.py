@@ -44,6 +44,10 @@ SIGNATURES = {
     "fdb_peer_comm_floats": (_i64, []),
     "fdb_bcd_solve_peer": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _i32, _f32,
                                      _vp, _vp, _vp, _vp, _vp, C.c_uint32, _vp, _vp]),
+    "fdb_tile_plan_workspace_bytes": (_i64, [_i64, _i64, _i32]),
+    "fdb_tile_plan_counts": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _i64, _vp, _i64, _vp, _vp, _vp]),
+    "fdb_tile_plan_build": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
+                                      _vp, _vp]),
     "fdb_comm_unique_id": (C.c_int, [C.c_char_p]),
     "fdb_comm_init": (C.c_int, [_i32, _i32, C.c_char_p, C.POINTER(_vp)]),
     "fdb_comm_destroy": (C.c_int, [_vp]),

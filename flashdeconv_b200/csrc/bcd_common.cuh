@@ -184,6 +184,7 @@ struct SweepComm {
     long long comm_off;             // float offset of the comm block
     int rank, world;
     unsigned seq;                   // sequence number of this sweep
+    int debug;                      // timing experiments only: bit 0 = do not wait for the peers, bit 1 = do not push rows
 };
 
 inline PlanView plan_view(const void *plan, int64_t n_ctas, int tile)

@@ -31,7 +31,7 @@ namespace fdb {
 // G[2m][2m+1] beta_old and G[2m+1][2m] beta_new are scalar FFMAs in the short serial tail.  Columns are walked from
 // the least to the most recently updated one, so only the last links of the two chains wait for the previous pair.
 // PADC = trailing all-padding columns (Kp - K >= PADC) left out at compile time.
-template <int KP, int NW, int MINB, int PADC>
+template <int KP, int NW, int MINB, int PADC, bool COMM>
 __global__ void __launch_bounds__(NW * 32, MINB)
 bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPairArg<KP> G,
                    const float *__restrict__ beta_in, float *__restrict__ beta_out,
@@ -54,9 +54,10 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
     __shared__ int s_last;
 
     if (*reinterpret_cast<volatile int *>(&state->converged)) return;      // uniform across the grid (and across ranks)
-    const bool comm_on = comm.world > 1;
+    // COMM = false (single GPU) compiles the multi-GPU extension out: the loop below is the round-1 kernel unchanged
+    const bool comm_on = COMM && comm.world > 1;
     const int n_push_patches = comm_on ? __ldg(comm.n_boundary) : 0;
-    auto patch_at = [&](int pi) { return comm.patch_order ? __ldg(comm.patch_order + pi) : pi; };
+    auto patch_at = [&](int pi) { return (COMM && comm.patch_order) ? __ldg(comm.patch_order + pi) : pi; };
 
     // Range of the fp16 gather tile.  Every |beta_in| is at most last_max_abs + last_max_diff (max|beta| of the sweep
     // before plus the largest step it took; fdb_bcd_init seeds 1/K), so with 2^x <= bound < 2^(x+1) the tile stores
@@ -316,7 +317,7 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
             if (p < n_rows) st4(beta_out + (size_t)p * KP + 4 * q, ld4(c_tile + L::at(wrow + lr, q)));
         }
         // ---------------- boundary rows -> the neighbouring tiles' halo slots (peer memory), from registers
-        if (pi < n_push_patches && my_row < n_rows) {
+        if (COMM && pi < n_push_patches && my_row < n_rows && !(comm.debug & 2)) {
             const int pe = __ldg(comm.push_ptr + my_row + 1);
             for (int u = __ldg(comm.push_ptr + my_row); u < pe; ++u) {
                 const int2 ent = __ldg(comm.push_ent + u);
@@ -325,10 +326,12 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
                 for (int q = 0; q < Q; ++q)
                     st4(dst + 4 * q, make_float4(b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]));
             }
+            // this thread's peer writes are ordered before the CTA's arrival (barrier + thread 0's fence below) and, through
+            // the arrival counter and the last CTA's release, before the flag the peers acquire
+            if (pe > __ldg(comm.push_ptr + my_row)) __threadfence_system();
         }
         patch = next;
     }
-    if (comm_on) __threadfence_system();                  // this thread's peer writes before the CTA's arrival below
 
     const unsigned wd = __reduce_max_sync(kFull, __float_as_uint(dmax));
     const unsigned wa = __reduce_max_sync(kFull, __float_as_uint(amax));
@@ -372,7 +375,7 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
         for (;;) {
             unsigned v;
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + peer) : "memory");
-            if ((int)(v - comm.seq) >= 0) break;
+            if ((int)(v - comm.seq) >= 0 || (comm.debug & 1)) break;
             if (clock64() - t0 > 120000000000LL) { s_timeout = 1; break; }                       // ~60 s: a peer is gone
         }
     }
@@ -424,7 +427,7 @@ int launch_sweep_p(const float *h, const GramArg<KP> &G, int n_types, const floa
         cm = SweepComm();
         cm.patch_order = nullptr; cm.n_boundary = nullptr; cm.push_ptr = nullptr; cm.push_ent = nullptr;
         for (int p = 0; p < kMaxRanks; ++p) cm.peer_base[p] = nullptr;
-        cm.out_off = cm.comm_off = 0; cm.rank = 0; cm.world = 1; cm.seq = 0u;
+        cm.out_off = cm.comm_off = 0; cm.rank = 0; cm.world = 1; cm.seq = 0u; cm.debug = 0;
     }
     auto run_p = [&](auto kern) -> int {
         int resident = 0;
@@ -440,10 +443,16 @@ int launch_sweep_p(const float *h, const GramArg<KP> &G, int n_types, const floa
     };
     // trailing padding columns (Kp - K, rounded down to even) are left out at compile time
     const int pad = KP - n_types;
-    if (pad >= 6) return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 6>);
-    if (pad >= 4) return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 4>);
-    if (pad >= 2) return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 2>);
-    return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 0>);
+    if (comm != nullptr) {
+        if (pad >= 6) return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 6, true>);
+        if (pad >= 4) return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 4, true>);
+        if (pad >= 2) return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 2, true>);
+        return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 0, true>);
+    }
+    if (pad >= 6) return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 6, false>);
+    if (pad >= 4) return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 4, false>);
+    if (pad >= 2) return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 2, false>);
+    return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 0, false>);
 }
 
 }  // namespace fdb

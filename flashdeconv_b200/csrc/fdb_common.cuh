@@ -73,6 +73,11 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// device-wide exclusive scan of int32 (graph.cu): out has n + 1 entries (out[n] = total), `in` and `out` may alias;
+// block_sums needs scan_blocks(n) words
+int exclusive_scan(const int32_t *in, int64_t n, int32_t *out, int32_t *block_sums, cudaStream_t st);
+int64_t scan_blocks(int64_t n);
+
 template <typename IndPtr>
 __device__ __forceinline__ int64_t load_ptr(const IndPtr *p, int64_t i) { return (int64_t)p[i]; }
 

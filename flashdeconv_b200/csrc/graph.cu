@@ -183,8 +183,8 @@ scan_apply_kernel(const int32_t *__restrict__ in, int64_t n, const int32_t *__re
     }
 }
 
-// out has n + 1 entries (out[n] = total).  `in` and `out` may alias.
-static int exclusive_scan(const int32_t *in, int64_t n, int32_t *out, int32_t *block_sums, cudaStream_t st)
+// out has n + 1 entries (out[n] = total).  `in` and `out` may alias.  (Also used by tile.cu.)
+int exclusive_scan(const int32_t *in, int64_t n, int32_t *out, int32_t *block_sums, cudaStream_t st)
 {
     if (n == 0) {
         FDB_CUDA(cudaMemsetAsync(out, 0, 4, st));
@@ -198,7 +198,7 @@ static int exclusive_scan(const int32_t *in, int64_t n, int32_t *out, int32_t *b
     FDB_LAUNCH_CHECK("exclusive_scan");
     return FDB_OK;
 }
-static int64_t scan_blocks(int64_t n) { return ceil_div(n > 0 ? n : 1, kScanTile); }
+int64_t scan_blocks(int64_t n) { return ceil_div(n > 0 ? n : 1, kScanTile); }
 
 // ---------------------------------------------------------------- cell sort
 __global__ void __launch_bounds__(256)

@@ -155,6 +155,7 @@ FDB_API int fdb_bcd_solve_peer(const float *h, const float *host_gram, void *con
     cm.comm_off = off_comm;
     cm.rank = rank;
     cm.world = world;
+    cm.debug = getenv("FDB_PEER_DEBUG") ? atoi(getenv("FDB_PEER_DEBUG")) : 0;
     int64_t cur = off_a, nxt = off_b;
     const int chunks = kp / 4;
     for (int it = 0; it < max_iter; ++it) {

@@ -177,18 +177,20 @@ def plan_tile_device(indptr, indices, nnz: int, bounds: List[Tuple[int, int]], r
     # where my boundary rows live in each peer's buffers: after its own rows, behind the rows of lower ranks
     base = t.tensor([(bounds[q][1] - bounds[q][0]) + sum(counts[r][q] for r in range(rank)) for q in range(R)],
                     device=dev, dtype=i64)
-    my = flags[lo:hi].to(i64)                                           # n_own x R
-    qrank = t.cumsum(my, 0) - my
-    push_cnt = my.sum(1)
+    my = flags[lo:hi].t().contiguous().to(i64)                          # R x n_own (scans run along the last dim)
+    qrank = t.cumsum(my, 1) - my                                        # rank of row i among my rows that peer q needs
+    push_cnt = my.sum(0)
     push_ptr = t.zeros(n_own + 1, device=dev, dtype=i64)
     t.cumsum(push_cnt, 0, out=push_ptr[1:])
-    within = t.cumsum(my, 1) - my
+    within = t.zeros_like(my)                                           # entries of lower peers in the same row
+    for q in range(1, R):
+        within[q] = within[q - 1] + my[q - 1]
     T = sum(counts[rank])
-    tgt = t.where(my > 0, push_ptr[:-1, None] + within, t.full_like(my, T)).flatten()
+    tgt = t.where(my > 0, push_ptr[None, :-1] + within, t.full_like(my, T)).flatten()
     ent = t.zeros((T + 1, 2), device=dev, dtype=i32)
-    peers = t.arange(R, device=dev, dtype=i32).expand(n_own, R).reshape(-1)
+    peers = t.arange(R, device=dev, dtype=i32)[:, None].expand(R, n_own).reshape(-1)
     ent[:, 0].scatter_(0, tgt, peers)
-    ent[:, 1].scatter_(0, tgt, (base[None, :] + qrank).to(i32).flatten())
+    ent[:, 1].scatter_(0, tgt, (base[:, None] + qrank).to(i32).flatten())
     # halo rows: the outside neighbours of my rows, ascending global position (= grouped by owner)
     nbr = idx[e0:e1]
     outside = (nbr < lo) | (nbr >= hi)
@@ -215,6 +217,57 @@ def plan_tile_device(indptr, indices, nnz: int, bounds: List[Tuple[int, int]], r
     return DeviceTilePlan(rank, lo, hi, n_own, n_halo, cap_rows, (ptr[lo:hi + 1] - e0).to(i32).contiguous(),
                           local.contiguous(), halo_global[:n_halo], push_ptr.to(i32).contiguous(),
                           ent[: max(T, 1)].contiguous(), order, n_boundary.to(i32).reshape(1), recv)
+
+
+def plan_tile_native(indptr, indices, nnz: int, bounds: List[Tuple[int, int]], rank: int) -> DeviceTilePlan:
+    """`plan_tile_device` through libfdb200 (csrc/tile.cu): three kernels + scans, one host read of the R x R
+    boundary-count matrix.  This is what TiledPath uses on the GPU."""
+    import torch
+    from . import _native
+    from .pipeline import _ptr, _stream
+    lib, check, t = _native.lib, _native.check, torch
+    dev = indptr.device
+    n = int(indptr.numel()) - 1
+    R = len(bounds)
+    lo, hi = bounds[rank]
+    n_own = hi - lo
+    n_own_max = max(b[1] - b[0] for b in bounds)
+    hb = (C.c_int32 * (R + 1))(*([b[0] for b in bounds] + [n]))
+    ws_bytes = int(lib.fdb_tile_plan_workspace_bytes(n, n_own_max, R))
+    ws = t.empty(ws_bytes, dtype=t.uint8, device=dev)
+    hc = (C.c_int64 * (R * R))()
+    he = (C.c_int64 * 2)()
+    st = _stream(t)
+    check(lib.fdb_tile_plan_counts(_ptr(indptr), _ptr(indices), n, hb, R, rank, n_own_max, _ptr(ws), ws_bytes, hc, he, st),
+          "tile_plan_counts")
+    counts = [[int(hc[r * R + q]) for q in range(R)] for r in range(R)]
+    nnz_local = int(he[1] - he[0])
+    n_halo_of = [sum(counts[r][q] for r in range(R)) for q in range(R)]
+    n_halo = n_halo_of[rank]
+    cap_rows = max(max((b[1] - b[0]) + n_halo_of[q] for q, b in enumerate(bounds)), 1)
+    recv, first = [], 0
+    for r in range(R):
+        if r != rank and counts[r][rank] > 0:
+            recv.append((r, first, counts[r][rank]))
+        first += counts[r][rank]
+    base = (C.c_int64 * R)(*[(bounds[q][1] - bounds[q][0]) + sum(counts[r][q] for r in range(rank)) for q in range(R)])
+    T = sum(counts[rank])
+    n_patches = max(-(-n_own // 128), 1)
+    i32 = t.int32
+    local_ptr = t.empty(n_own + 1, dtype=i32, device=dev)
+    local_idx = t.empty(max(nnz_local, 1), dtype=i32, device=dev)
+    halo_global = t.empty(max(n_halo, 1), dtype=t.int64, device=dev)
+    push_ptr = t.empty(n_own + 1, dtype=i32, device=dev)
+    push_ent = t.empty((max(T, 1), 2), dtype=i32, device=dev)
+    order = t.empty(n_patches, dtype=i32, device=dev)
+    n_boundary = t.empty(1, dtype=i32, device=dev)
+    check(lib.fdb_tile_plan_build(_ptr(indptr), _ptr(indices), n, hb, R, rank, n_own_max, base, _ptr(ws), ws_bytes,
+                                  _ptr(local_ptr), _ptr(local_idx), _ptr(halo_global), _ptr(push_ptr), _ptr(push_ent),
+                                  _ptr(order), _ptr(n_boundary), st), "tile_plan_build")
+    plan = DeviceTilePlan(rank, lo, hi, n_own, n_halo, cap_rows, local_ptr, local_idx, halo_global[:n_halo], push_ptr,
+                          push_ent, order, n_boundary, recv)
+    plan._keepalive = ws                                  # the kernels above are still in flight
+    return plan
 
 
 def halo_exchange(beta, plan: TilePlan, pack: Callable, group=None, tag: int = 0):
@@ -312,7 +365,7 @@ class TiledPath:
         n = int(self.graph.order.numel())
         self.bounds = tile_bounds(n, self.world)
         if self.mode == "peer":
-            self.plan = plan_tile_device(self.graph.indptr, self.graph.indices, self.graph.nnz, self.bounds, self.rank)
+            self.plan = plan_tile_native(self.graph.indptr, self.graph.indices, self.graph.nnz, self.bounds, self.rank)
         else:
             self.plan = plan_tile(self.graph.indptr, self.graph.indices[: max(self.graph.nnz, 1)], self.bounds, self.rank)
         p = self.plan

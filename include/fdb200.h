@@ -222,6 +222,24 @@ int fdb_bcd_solve_tiled(const float *h, const float *host_gram, float *beta_a, f
                         const int64_t *host_send_count, float *const *host_send_buf, void *comm,
                         const void *plan, void *stream);
 
+/* Partition of the solve over `world` ranks, derived on the device from the replicated global graph (tile order).
+ * Rank r owns positions [host_bounds[r], host_bounds[r + 1]).  Phase 1 (fdb_tile_plan_counts, identical on every rank,
+ * ONE stream synchronisation): host_counts[r * world + q] = number of rows of r with a neighbour owned by q, and
+ * host_e = {indptr[lo], indptr[hi]} of `rank`.  From the counts the host derives every rank's halo size, the
+ * capacity of the symmetric beta buffers and host_base[q] = n_own(q) + sum_{r < rank} counts[r][q], the first row
+ * of peer q's buffers that receives this rank's boundary rows.  Phase 2 (fdb_tile_plan_build, no synchronisation)
+ * writes this rank's local adjacency (own rows 0 .. n_own-1, halo rows after them in ascending global position),
+ * the halo row list, the per-row push entries, and the patch order / boundary-patch count the fused sweep kernel
+ * consumes (see fdb_bcd_solve_peer).  Same workspace for both phases (fdb_tile_plan_workspace_bytes). */
+int64_t fdb_tile_plan_workspace_bytes(int64_t n, int64_t n_own_max, int32_t world);
+int fdb_tile_plan_counts(const int32_t *indptr, const int32_t *indices, int64_t n, const int32_t *host_bounds,
+                         int32_t world, int32_t rank, int64_t n_own_max, void *workspace, int64_t workspace_bytes,
+                         int64_t *host_counts, int64_t *host_e, void *stream);
+int fdb_tile_plan_build(const int32_t *indptr, const int32_t *indices, int64_t n, const int32_t *host_bounds,
+                        int32_t world, int32_t rank, int64_t n_own_max, const int64_t *host_base, void *workspace,
+                        int64_t workspace_bytes, int32_t *local_ptr, int32_t *local_idx, int64_t *halo_global,
+                        int32_t *push_ptr, void *push_ent, int32_t *patch_order, int32_t *n_boundary, void *stream);
+
 /* Peer-memory form of fdb_bcd_solve_tiled: no NCCL on the data path.  Every rank's beta buffers live in a
  * symmetric allocation mapped by all peers; host_peer_base[p] is rank p's base pointer as seen from THIS
  * process.  Layout (floats): beta_a [cap_rows x Kp], beta_b [cap_rows x Kp], comm [fdb_peer_comm_floats()],

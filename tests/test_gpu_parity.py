@@ -548,6 +548,30 @@ def test_tiled_path_two_ranks_equals_device_path(mode):
     assert "OK" in out.stdout and f"[{mode}]" in out.stdout
 
 
+def test_native_tile_plan_equals_torch_plan():
+    """csrc/tile.cu against the torch statement of the same partition (tiling.plan_tile_device, itself checked against
+    plan_tile on the CPU): identical local adjacency, halo rows, push entries and patch order on every rank."""
+    import torch
+    from flashdeconv_b200 import pipeline as pl, tiling
+    rng = np.random.default_rng(5)
+    for n, world in ((3000, 2), (40000, 8), (777, 3), (20000, 5)):
+        side = int(np.ceil(np.sqrt(n)))
+        c = np.stack(np.meshgrid(np.arange(side), np.arange(side)), -1).reshape(-1, 2)[:n] + rng.normal(0, 0.1, (n, 2))
+        g = pl.build_graph(torch.from_numpy(c).cuda(), "knn", 6)
+        bounds = tiling.tile_bounds(n, world)
+        for r in range(world):
+            a = tiling.plan_tile_device(g.indptr, g.indices, g.nnz, bounds, r)
+            b = tiling.plan_tile_native(g.indptr, g.indices, g.nnz, bounds, r)
+            torch.cuda.synchronize()
+            assert (a.n_own, a.n_halo, a.cap_rows, a.recv) == (b.n_own, b.n_halo, b.cap_rows, b.recv)
+            nl = int(a.indptr[-1])
+            assert torch.equal(a.indptr, b.indptr) and torch.equal(a.indices[:nl], b.indices[:nl])
+            assert torch.equal(a.halo_global, b.halo_global) and torch.equal(a.push_ptr, b.push_ptr)
+            T = int(a.push_ptr[-1])
+            assert torch.equal(a.push_ent[:T], b.push_ent[:T])
+            assert torch.equal(a.patch_order, b.patch_order) and int(a.n_boundary) == int(b.n_boundary)
+
+
 # ---------------------------------------------------------------- f1: gene moments on the device
 def test_device_gene_selection_equals_host_selection():
     """float64 moment pass on the GPU -> the very same HVG/marker set as the host (= reference) code"""

@@ -5,10 +5,6 @@ NG=${NG:-2}
 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 600 -k "tiled" 2>&1 | tail -12 | tee gpurun_out/pytest_tiled.log
 for N in ${NS:-1 $NG}; do
   if [ "$N" = "1" ]; then L="python"; else L="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611"; fi
-  timeout 900 $L bench.py --gpus $N --steps 5 --config ${CFG:-C3} --no-cpu-baseline ${BENCH_ARGS:---no-c5} 2>gpurun_out/multi_${CFG:-C3}_g$N.err | tee gpurun_out/multi_${CFG:-C3}_g$N.json | python -c "
-import sys, json
-d = json.loads(sys.stdin.readline())
-print('N=$N ms_per_step', round(d['ms_per_step'],3), {k: round(x,3) for k,x in d['stage_ms'].items()}, 'sweep_us', round(1e3*d['roofline']['ms_per_launch'],2), 'e2e_ms', d['e2e'].get('ms_per_step'), 'h2d', d['e2e'].get('h2d_bytes_per_step'), 'obj', d['final_objective'])
-if 'c5' in d: print('   c5', d['c5']['ms_per_step'], d['c5']['stage_ms'], d['c5']['sweep_us'])"
+  timeout 900 $L bench.py --gpus $N --steps 5 --config ${CFG:-C3} --no-cpu-baseline ${BENCH_ARGS:---no-c5} 2>gpurun_out/multi_${CFG:-C3}_g$N.err | tee gpurun_out/multi_${CFG:-C3}_g$N.json | python tools/jline.py "N=$N"
   tail -3 gpurun_out/multi_${CFG:-C3}_g$N.err
 done
