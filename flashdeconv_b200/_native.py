@@ -26,6 +26,8 @@ SIGNATURES = {
                                           _vp, _vp, _i32, _vp, _vp, _vp]),
     "fdb_sketch_linear_contract_csr": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _i32,
                                           _vp, _vp, _i32, _vp, _vp, _vp]),
+    "fdb_sketch_contract_scatter_csr": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _i32,
+                                                  _i32, _i32, _vp, _vp, _vp, _vp]),
     "fdb_gene_sums_csr": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "fdb_graph_workspace_bytes": (_i64, [_i64, _i32]),
     "fdb_graph_build": (C.c_int, [_vp, _i64, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _i64,

@@ -435,7 +435,12 @@ int launch_sweep_p(const float *h, const GramArg<KP> &G, int n_types, const floa
         FDB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, tile, smem));
         // FDB_SWEEP_MAX_CTAS caps the persistent grid (tests: several patches per CTA on small problems)
         static const int cap = getenv("FDB_SWEEP_MAX_CTAS") ? std::max(atoi(getenv("FDB_SWEEP_MAX_CTAS")), 1) : 1 << 30;
-        const int grid = (int)std::min<int64_t>(std::min<int64_t>(n_ctas, cap), (int64_t)kNumSM * std::max(resident, 1));
+        // persistent grid: as many CTAs as are resident, but balanced -- with R = ceil(patches / slots) rounds every CTA
+        // walks R (or R - 1) patches instead of leaving a ragged last round to a few CTAs (matters when a rank's tile
+        // is barely more than one round: 977 patches on 888 slots at 8 GPUs)
+        const int64_t slots = (int64_t)kNumSM * std::max(resident, 1);
+        const int64_t rounds = std::max<int64_t>(ceil_div(n_ctas, slots), 1);
+        const int grid = (int)std::min<int64_t>(std::min<int64_t>(n_ctas, cap), ceil_div(n_ctas, rounds));
         kern<<<grid, tile, smem, st>>>(h, P, beta_in, beta_out, indptr, indices, pv, (int)n_rows, n_types, lam, rho, tol,
                                        finalize, state, (int)n_ctas, cm);
         FDB_LAUNCH_CHECK("bcd_sweep_p_kernel");

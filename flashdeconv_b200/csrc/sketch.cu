@@ -263,6 +263,18 @@ __device__ __forceinline__ float sk_xform(float v, float scale)
 
 constexpr int kV5List = 256;        // compacted selected entries per flush (8-byte records)
 
+// Multi-GPU output scatter of the fused kernel (world <= 1: unused).  Each rank sketches a slice of INPUT rows (the rows
+// it uploaded) while the solve wants H in TILE order, sharded by spatial tile: the output row index delivered by
+// row_map is a global tile position p; the row is written straight into the H / ||y_s||^2 buffers of the rank that owns
+// p (peer memory over NVLink) -- the sketch and its all-to-all in one kernel.
+constexpr int kSketchMaxRanks = 16;
+struct SketchScatter {
+    int world;
+    int32_t bounds[kSketchMaxRanks + 1];      // rank q owns positions [bounds[q], bounds[q + 1])
+    float *h[kSketchMaxRanks];                // q's H buffer (own rows x Kp), as mapped in THIS process
+    float *ysq[kSketchMaxRanks];
+};
+
 // TAB = true: u16 gene -> slot table (2 bytes per gene); TAB = false: one membership bit per gene + a rank prefix per
 // 32-gene word (slot = prefix + popc of the bits below), for wide gene axes / wide rows where the table does not fit
 // next to X_s^T -- the list then carries the gene and the slot is computed for the selected entries only.
@@ -273,7 +285,8 @@ sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
                           const int32_t *__restrict__ gene_bucket, const float *__restrict__ gene_weight,
                           int d, const float *__restrict__ x_sketch_t, int kp,
                           const int32_t *__restrict__ row_map, const int32_t *__restrict__ row_ids,
-                          float *__restrict__ h, float *__restrict__ ysq, int linear)
+                          float *__restrict__ h, float *__restrict__ ysq, int linear,
+                          const __grid_constant__ SketchScatter sc)
 {
     constexpr int XS = NK * 32;                                                         // floats per staged X_s^T row
     constexpr int PF = NK == 1 ? 16 : 8;      // register-prefetched chunks of 32 entries (wide rows hold 64 accumulators)
@@ -626,6 +639,14 @@ sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
         }
         sq = warp_sum(sq);
         float *out = h + orow * kp;
+        float *out_sq = ysq + orow;
+        if (sc.world > 1) {                                               // orow is a global tile position: find its owner
+            int q = 0;
+            for (int r = 1; r < sc.world; ++r) q += orow >= sc.bounds[r];
+            const int64_t local = orow - sc.bounds[q];
+            out = sc.h[q] + local * kp;
+            out_sq = sc.ysq[q] + local;
+        }
         if (lane < 8) {                                                   // lane j: chunk j (and 8 + j) of H[orow]
             if (4 * lane < kp) {
                 float4 o;
@@ -640,7 +661,7 @@ sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
                 *reinterpret_cast<float4 *>(out + 32 + 4 * lane) = o;
             }
         }
-        if (lane == 0) ysq[orow] = sq;
+        if (lane == 0) *out_sq = sq;
         __syncwarp();
         it = it_next; s = s2; len = len2; row = row2;
     }
@@ -790,8 +811,12 @@ template <typename IndPtr, int NK>
 static int launch_fused(const void *indptr, const int32_t *indices, const float *counts,
                         int64_t n_spots, int n_genes, int n_selected, const int32_t *gene_bucket,
                         const float *gene_weight, int d, const float *x_sketch_t, int kp, const int32_t *row_map,
-                        const int32_t *row_ids, float *h, float *ysq, int linear, cudaStream_t st)
+                        const int32_t *row_ids, float *h, float *ysq, int linear, cudaStream_t st,
+                        const SketchScatter *scatter = nullptr)
 {
+    SketchScatter sc;
+    if (scatter) sc = *scatter;
+    else sc.world = 1;
     // production: v5 (v3 structure + conflict-free XOR-phased AXPY, select-free reduction, integer atomics); the u16
     // gene -> slot table when it leaves room for at least 12 warps, else the membership bitmap + rank prefix
     if (n_selected >= 0 && getenv("FDB_SKETCH_V1") == nullptr) {
@@ -815,7 +840,7 @@ static int launch_fused(const void *indptr, const int32_t *indices, const float 
                 FDB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 kern<<<grid, warps * 32, smem, st>>>((const IndPtr *)indptr, indices, counts, n_spots, n_genes, n_selected,
                                                      gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq,
-                                                     linear);
+                                                     linear, sc);
                 FDB_LAUNCH_CHECK("sketch_contract_v5_kernel");
                 return FDB_OK;
             };
@@ -825,6 +850,10 @@ static int launch_fused(const void *indptr, const int32_t *indices, const float 
             return linear ? go(sketch_contract_v5_kernel<IndPtr, NK, false, false>)
                           : go(sketch_contract_v5_kernel<IndPtr, NK, true, false>);
         }
+    }
+    if (scatter) {
+        set_error("the scattering sketch needs the shared-memory kernel (n_selected known, tables that fit)");
+        return FDB_ERR_UNSUPPORTED;
     }
     // fallback: v1 (tables in global memory) for very wide gene axes / sketches
     const size_t xs_bytes = (size_t)d * NK * 32 * 4;
@@ -854,22 +883,23 @@ static int launch_fused(const void *indptr, const int32_t *indices, const float 
 static int sketch_contract_impl(const void *indptr, int indptr_is_int64, const int32_t *indices, const float *counts,
                                 int64_t n_spots, int32_t n_genes, const int32_t *gene_bucket, const float *gene_weight,
                                 int32_t d, const float *x_sketch_t, int32_t n_types, const int32_t *row_map,
-                                const int32_t *row_ids, int32_t n_selected, float *h, float *ysq, int linear, void *stream)
+                                const int32_t *row_ids, int32_t n_selected, float *h, float *ysq, int linear, void *stream,
+                                const SketchScatter *scatter = nullptr)
 {
     FDB_REQUIRE(n_spots >= 0 && n_genes >= 0, "negative shape");
     FDB_REQUIRE(d > 0 && d % 4 == 0, "sketch_dim must be a positive multiple of 4, got %d", d);
     FDB_REQUIRE(n_types > 0 && n_types <= FDB_MAX_TYPES, "n_types must be in [1, %d], got %d", FDB_MAX_TYPES, n_types);
     if (n_spots == 0) return FDB_OK;
-    FDB_REQUIRE(indptr && gene_bucket && gene_weight && x_sketch_t && h && ysq, "null pointer");
+    FDB_REQUIRE(indptr && gene_bucket && gene_weight && x_sketch_t && ((h && ysq) || scatter), "null pointer");
     const int kp = fdb_padded_types(n_types);
     cudaStream_t st = (cudaStream_t)stream;
     if (kp <= 32)
         return indptr_is_int64
-                   ? launch_fused<int64_t, 1>(indptr, indices, counts, n_spots, n_genes, n_selected, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, linear, st)
-                   : launch_fused<int32_t, 1>(indptr, indices, counts, n_spots, n_genes, n_selected, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, linear, st);
+                   ? launch_fused<int64_t, 1>(indptr, indices, counts, n_spots, n_genes, n_selected, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, linear, st, scatter)
+                   : launch_fused<int32_t, 1>(indptr, indices, counts, n_spots, n_genes, n_selected, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, linear, st, scatter);
     return indptr_is_int64
-               ? launch_fused<int64_t, 2>(indptr, indices, counts, n_spots, n_genes, n_selected, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, linear, st)
-               : launch_fused<int32_t, 2>(indptr, indices, counts, n_spots, n_genes, n_selected, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, linear, st);
+               ? launch_fused<int64_t, 2>(indptr, indices, counts, n_spots, n_genes, n_selected, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, linear, st, scatter)
+               : launch_fused<int32_t, 2>(indptr, indices, counts, n_spots, n_genes, n_selected, gene_bucket, gene_weight, d, x_sketch_t, kp, row_map, row_ids, h, ysq, linear, st, scatter);
 }
 
 extern "C" __attribute__((visibility("default"))) int fdb_sketch_contract_csr(const void *indptr, int indptr_is_int64, const int32_t *indices,
@@ -890,6 +920,27 @@ extern "C" __attribute__((visibility("default"))) int fdb_sketch_linear_contract
 {
     return sketch_contract_impl(indptr, indptr_is_int64, indices, counts, n_spots, n_genes, gene_bucket, gene_weight, d,
                                 x_sketch_t, n_types, row_map, row_ids, n_selected, h, ysq, 1, stream);
+}
+
+extern "C" __attribute__((visibility("default"))) int fdb_sketch_contract_scatter_csr(
+    const void *indptr, int indptr_is_int64, const int32_t *indices, const float *counts, int64_t n_spots, int32_t n_genes,
+    const int32_t *gene_bucket, const float *gene_weight, int32_t d, const float *x_sketch_t, int32_t n_types,
+    const int32_t *row_map, int32_t n_selected, int32_t linear, int32_t world, const int32_t *host_bounds,
+    void *const *host_h, void *const *host_ysq, void *stream)
+{
+    FDB_REQUIRE(world >= 1 && world <= kSketchMaxRanks && host_bounds && host_h && host_ysq && row_map, "bad scatter arguments");
+    SketchScatter sc;
+    sc.world = world;
+    for (int q = 0; q <= kSketchMaxRanks; ++q) sc.bounds[q] = host_bounds[std::min(q, (int)world)];
+    for (int q = 0; q < kSketchMaxRanks; ++q) {
+        sc.h[q] = q < world ? (float *)host_h[q] : nullptr;
+        sc.ysq[q] = q < world ? (float *)host_ysq[q] : nullptr;
+    }
+    if (world == 1)      // plain form: row_map indexes the single rank's buffers
+        return sketch_contract_impl(indptr, indptr_is_int64, indices, counts, n_spots, n_genes, gene_bucket, gene_weight, d,
+                                    x_sketch_t, n_types, row_map, nullptr, n_selected, sc.h[0], sc.ysq[0], linear, stream);
+    return sketch_contract_impl(indptr, indptr_is_int64, indices, counts, n_spots, n_genes, gene_bucket, gene_weight, d,
+                                x_sketch_t, n_types, row_map, nullptr, n_selected, nullptr, nullptr, linear, stream, &sc);
 }
 
 // per-gene sums of the raw counts (float64), for the per-gene scale of preprocess "pearson" (core/deconv.py:206-212)

@@ -298,7 +298,11 @@ class TiledPath:
     only the rank's tile is sketched and solved.  Results stay sharded on the device (`beta_own`, in tile
     order) until `gather_outputs` assembles float64 arrays in input order on every rank."""
 
-    def __init__(self, csr, coords_dev, tables, n_types: int, group=None):
+    def __init__(self, csr, coords_dev, tables, n_types: int, group=None, slice_rows: Optional[Tuple[int, int]] = None):
+        """`csr` is either the full (replicated) matrix -- every rank then sketches the rows of its own tile -- or, with
+        slice_rows = (a, b), only input rows [a, b): the rank sketches THOSE rows and the fused kernel writes every
+        H row into the buffers of the rank that owns its tile position (peer memory), so that each rank uploads 1/R of
+        the counts.  The slices of all ranks must cover all rows exactly once."""
         import torch
         import torch.distributed as dist
         from . import _native, pipeline
@@ -307,6 +311,7 @@ class TiledPath:
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.csr, self.coords, self.tables, self.K = csr, coords_dev, tables, int(n_types)
+        self.slice_rows = slice_rows
         self.Kp = _native.padded_types(self.K)
         self.dev = csr.indices.device
         self.gene_bucket = torch.from_numpy(tables.gene_bucket).to(self.dev)
@@ -373,11 +378,15 @@ class TiledPath:
             p.indices = t.zeros(1, dtype=t.int32, device=self.dev)
         self.h = t.empty((max(p.n_own, 1), self.Kp), dtype=t.float32, device=self.dev)
         self.ysq = t.empty(max(p.n_own, 1), dtype=t.float32, device=self.dev)
+        if self.slice_rows is not None and self.mode != "peer":
+            raise RuntimeError("row-sliced inputs need the peer-memory mode (H rows are scattered over NVLink)")
         if self.mode == "peer":
             try:
                 self._setup_peer()
                 return self.graph
             except Exception as exc:          # no P2P mapping on this box: fall back to the NCCL loop
+                if self.slice_rows is not None:
+                    raise
                 import warnings
                 warnings.warn(f"peer-memory halo exchange unavailable ({exc!r}); using NCCL send/recv")
                 self.mode = "nccl"
@@ -391,12 +400,16 @@ class TiledPath:
         return self.graph
 
     def _setup_peer(self):
-        """Symmetric beta buffers (mapped by every peer), cached per (size, group)."""
+        """Symmetric buffers (mapped by every peer), cached per (size, group).  Layout in floats:
+        [beta_a cap x Kp][beta_b cap x Kp][comm][H own_max x Kp][ysq own_max]."""
         import torch.distributed._symmetric_memory as symm_mem
         t, p, dist = self.torch, self.plan, self.dist
         cap_rows = p.cap_rows
+        own_max = max(b[1] - b[0] for b in self.bounds)
         comm_floats = int(self.lib.fdb_peer_comm_floats())
-        total = 2 * cap_rows * self.Kp + comm_floats
+        off_h = 2 * cap_rows * self.Kp + comm_floats
+        off_ysq = off_h + own_max * self.Kp
+        total = off_ysq + ((own_max + 63) // 64) * 64
         key = (total, id(self.group))
         if key not in _SYMM_CACHE:
             buf = symm_mem.empty(total, dtype=t.float32, device=self.dev)
@@ -410,9 +423,28 @@ class TiledPath:
         self.cap_rows = cap_rows
         self.beta_a = self.symm_buf[: cap_rows * self.Kp].view(cap_rows, self.Kp)
         self.beta_b = self.symm_buf[cap_rows * self.Kp: 2 * cap_rows * self.Kp].view(cap_rows, self.Kp)
+        self.h = self.symm_buf[off_h: off_h + max(p.n_own, 1) * self.Kp].view(max(p.n_own, 1), self.Kp)
+        self.ysq = self.symm_buf[off_ysq: off_ysq + max(p.n_own, 1)]
+        self.peer_h = [ptr + 4 * off_h for ptr in self.peer_ptrs]
+        self.peer_ysq = [ptr + 4 * off_ysq for ptr in self.peer_ptrs]
 
     def stage_sketch(self):
         c, tb, p = self.csr, self.tables, self.plan
+        if self.slice_rows is not None:
+            a, b = self.slice_rows
+            if b > a:
+                R = self.world
+                hb = (C.c_int32 * (R + 1))(*([x[0] for x in self.bounds] + [int(self.graph.order.numel())]))
+                ph = (C.c_void_p * R)(*self.peer_h)
+                py = (C.c_void_p * R)(*self.peer_ysq)
+                self._row_map = self.graph.rank[a:b].contiguous()
+                self.check(self.lib.fdb_sketch_contract_scatter_csr(
+                    self.pl._ptr(c.indptr), int(c.indptr.dtype == self.torch.int64), self.pl._ptr(c.indices),
+                    self.pl._ptr(c.data), b - a, c.shape[1], self.pl._ptr(self.gene_bucket), self.pl._ptr(self.gene_weight),
+                    self.d_dev, self.pl._ptr(self.x_sketch_t), self.K, self.pl._ptr(self._row_map), int(len(tb.bucket)),
+                    int(tb.linear), R, hb, ph, py, self._stream()), "sketch_contract_scatter_csr")
+            self._row_ids = self.graph.order[p.lo:p.hi].contiguous()
+            return
         if p.n_own == 0:
             return
         row_ids = self.graph.order[p.lo:p.hi].contiguous()
@@ -519,23 +551,31 @@ class TiledPath:
         return 0.5 * (yty - 2.0 * cross + quad) + 0.5 * lam * lap + rho_scaled * l1
 
     def finish_sharded(self, beta_dev):
-        """float64 beta / proportions for this rank's rows, written at their INPUT-order row of full-size buffers."""
+        """float64 beta / proportions of this rank's rows, compact and in TILE order: (n_own_max x 2K), beta | proportions."""
         t, p, pl = self.torch, self.plan, self.pl
-        n = int(self.graph.order.numel())
-        if not hasattr(self, "_b64"):
-            self._b64 = t.empty((n, self.K), dtype=t.float64, device=self.dev)
-            self._p64 = t.empty((n, self.K), dtype=t.float64, device=self.dev)
-        self._b64.zero_()
-        self._p64.zero_()
+        own_max = max(b[1] - b[0] for b in self.bounds)
+        if not hasattr(self, "_own64") or self._own64.shape[0] != own_max:
+            self._own64 = t.zeros((2, own_max, self.K), dtype=t.float64, device=self.dev)
         if p.n_own:
-            self.check(self.lib.fdb_finish(pl._ptr(beta_dev), pl._ptr(self._row_ids), p.n_own, self.K,
-                                           pl._ptr(self._b64), pl._ptr(self._p64), self._stream()), "finish")
-        return self._b64, self._p64
+            self.check(self.lib.fdb_finish(pl._ptr(beta_dev), pl._ptr(None), p.n_own, self.K, pl._ptr(self._own64[0]),
+                                           pl._ptr(self._own64[1]), self._stream()), "finish")
+        return self._own64[0, : p.n_own], self._own64[1, : p.n_own]
 
     def gather_outputs(self):
-        """Every rank contributes its rows (zeros elsewhere): one SUM all-reduce assembles the full arrays."""
-        self.dist.all_reduce(self._b64, op=self.dist.ReduceOp.SUM, group=self.group)
-        self.dist.all_reduce(self._p64, op=self.dist.ReduceOp.SUM, group=self.group)
+        """All-gather of the ranks' own rows (tile order), then one un-permute to input order on every rank."""
+        t = self.torch
+        n = int(self.graph.order.numel())
+        own_max = self._own64.shape[1]
+        allr = t.empty((self.world, 2, own_max, self.K), dtype=t.float64, device=self.dev)
+        self.dist.all_gather_into_tensor(allr, self._own64, group=self.group)
+        if not hasattr(self, "_b64") or self._b64.shape[0] != n:
+            self._b64 = t.empty((n, self.K), dtype=t.float64, device=self.dev)
+            self._p64 = t.empty((n, self.K), dtype=t.float64, device=self.dev)
+        order = self.graph.order.long()
+        for q, (lo, hi) in enumerate(self.bounds):
+            if hi > lo:
+                self._b64.index_copy_(0, order[lo:hi], allr[q, 0, : hi - lo])
+                self._p64.index_copy_(0, order[lo:hi], allr[q, 1, : hi - lo])
         return self._b64, self._p64
 
     def run_resident(self, *, method="knn", k=6, radius=None, lam="auto", rho=0.01, max_iter=100, tol=1e-4,
@@ -554,7 +594,7 @@ class TiledPath:
 
         mark("graph", lambda: self.stage_graph(method, k, radius))
         mark("sketch", self.stage_sketch)
-        lam_used = self.lambda_auto() if isinstance(lam, str) else float(lam)
+        lam_used = self.lambda_auto() if (isinstance(lam, str) and lam == "auto") else float(lam)
         rho_s = self.rho_scaled(rho)
         mark("solve", lambda: self.stage_solve(lam_used, rho_s, max_iter, tol))
         n_iter, conv, rel = self.read_state()
@@ -568,17 +608,54 @@ class TiledPath:
         return b64, p64, info, lam_used
 
 
+def _host_row_slice(Y, a: int, b: int, dev):
+    """Rows [a, b) of the host counts as a DeviceCSR (rebased row pointers) + the bytes that crossed PCIe."""
+    import torch
+    from scipy import sparse
+    from . import pipeline
+    if isinstance(Y, pipeline.HostCSR):
+        e0, e1 = int(Y.indptr[a]), int(Y.indptr[b])
+        ptr = Y.indptr[a:b + 1].to(dev, non_blocking=True)
+        csr = pipeline.DeviceCSR(ptr - e0, Y.indices[e0:e1].to(dev, non_blocking=True),
+                                 Y.data[e0:e1].to(dev, non_blocking=True), (b - a, Y.shape[1]))
+    else:
+        if not sparse.issparse(Y):
+            Y = sparse.csr_matrix(np.asarray(Y)[a:b])
+            a, b = 0, Y.shape[0]
+        csr = pipeline.csr_to_device(Y.tocsr()[a:b])
+    nbytes = sum(int(x.numel() * x.element_size()) for x in (csr.indptr, csr.indices, csr.data))
+    return csr, nbytes
+
+
 def deconvolve_path_tiled(Y, X, coords, gene_idx, leverage, *, sketch_dim=512, lambda_spatial="auto",
                           rho_sparsity=0.01, spatial_method="knn", k_neighbors=6, radius=None, max_iter=100,
-                          tol=1e-4, random_state=0, pinned_out=False, group=None):
-    """Multi-GPU counterpart of pipeline.deconvolve_path: every rank passes the same HOST inputs, uploads them,
-    solves its tile and gets the full float64 outputs back (SUM all-reduce of the disjoint row sets)."""
+                          tol=1e-4, random_state=0, pinned_out=False, group=None, preprocess="log_cpm",
+                          y_col_mean=None):
+    """Multi-GPU counterpart of pipeline.deconvolve_path: every rank passes the same HOST inputs but uploads only its
+    1/R slice of the rows; the fused sketch kernel delivers each H row to the rank that owns its spatial tile (peer
+    memory), the ranks solve their tiles with per-sweep halo pushes, and the float64 outputs are all-gathered (own rows)
+    so that every rank returns the full arrays."""
     import torch
+    import torch.distributed as dist
     from . import pipeline
-    tables = pipeline.build_tables(X, gene_idx, leverage, sketch_dim, random_state, Y.shape[1])
-    csr = pipeline.csr_to_device(Y)
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if preprocess == "pearson" and y_col_mean is None:
+        raise ValueError("preprocess='pearson' on several GPUs needs y_col_mean (per-gene means of all spots)")
+    tables = pipeline.build_tables(X, gene_idx, leverage, sketch_dim, random_state, Y.shape[1], preprocess, y_col_mean)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n = Y.shape[0]
+    a, b = (n * rank) // world, (n * (rank + 1)) // world
     c = coords if torch.is_tensor(coords) else torch.from_numpy(np.ascontiguousarray(coords, dtype=np.float64))
-    path = TiledPath(csr, c.to(csr.indices.device, non_blocking=True), tables, np.asarray(X).shape[0], group)
+    coords_dev = c.to(dev, non_blocking=True)
+    mode = __import__("os").environ.get("FDB_TILED_MODE", "peer")
+    if mode == "peer":
+        csr, h2d = _host_row_slice(Y, a, b, dev)
+        path = TiledPath(csr, coords_dev, tables, np.asarray(X).shape[0], group, slice_rows=(a, b))
+    else:
+        csr = pipeline.csr_to_device(Y)
+        h2d = sum(int(x.numel() * x.element_size()) for x in (csr.indptr, csr.indices, csr.data))
+        path = TiledPath(csr, coords_dev, tables, np.asarray(X).shape[0], group)
+    h2d += int(coords_dev.numel() * coords_dev.element_size())
     b64, p64, info, lam = path.run_resident(method=spatial_method, k=k_neighbors, radius=radius, lam=lambda_spatial,
                                             rho=rho_sparsity, max_iter=max_iter, tol=tol, gather=True)
     path.close()
@@ -591,4 +668,7 @@ def deconvolve_path_tiled(Y, X, coords, gene_idx, leverage, *, sketch_dim=512, l
         beta, prop = hb.numpy(), hp.numpy()
     else:
         beta, prop = b64.cpu().numpy(), p64.cpu().numpy()
-    return pipeline.SolveResult(beta, prop, info, lam, path.graph, tables)
+    res = pipeline.SolveResult(beta, prop, info, lam, path.graph, tables)
+    res.h2d_bytes = h2d
+    res.d2h_bytes = int(beta.nbytes + prop.nbytes)
+    return res

@@ -97,6 +97,18 @@ int fdb_sketch_linear_contract_csr(const void *indptr, int indptr_is_int64, cons
                                    const float *x_sketch_t, int32_t n_types, const int32_t *row_map,
                                    const int32_t *row_ids, int32_t n_selected, float *h, float *ysq, void *stream);
 
+/* Multi-GPU form of the two calls above (linear != 0: the linear branches): this rank sketches the `n_spots` input rows
+ * of the CSR slice it holds; row_map[i] is the global TILE position of slice row i, and the row lands in the H / ysq
+ * buffers of the rank that owns that position (host_bounds[q] <= p < host_bounds[q + 1]) -- written over NVLink
+ * through the peer mappings host_h[q] / host_ysq[q] (as seen from this process; own rows x Kp floats, own rows floats).
+ * The sketch and its all-to-all in one kernel.  Needs n_selected >= 0. */
+int fdb_sketch_contract_scatter_csr(const void *indptr, int indptr_is_int64, const int32_t *indices,
+                                    const float *counts, int64_t n_spots, int32_t n_genes,
+                                    const int32_t *gene_bucket, const float *gene_weight, int32_t d,
+                                    const float *x_sketch_t, int32_t n_types, const int32_t *row_map,
+                                    int32_t n_selected, int32_t linear, int32_t world, const int32_t *host_bounds,
+                                    void *const *host_h, void *const *host_ysq, void *stream);
+
 /* Per-gene sums of the raw counts, float64, ACCUMULATED into sums[n_genes] (zero it first): the column means of
  * preprocess "pearson" (Y.mean(axis=0), core/deconv.py:207). */
 int fdb_gene_sums_csr(const int32_t *indices, const float *counts, int64_t nnz, int32_t n_genes, double *sums,

@@ -36,6 +36,12 @@ def main():
           and abs(lam - single.lambda_used) <= 1e-12 * lam)
     halo = tp.plan.n_halo
     tp.close()
+    # the host-input call: every rank uploads 1/R of the rows, H rows travel to their tile's owner over NVLink
+    if tp.mode == "peer":
+        res = tiling.deconvolve_path_tiled(ds.Y, ds.X, ds.coords, gene_idx, lev, sketch_dim=128, max_iter=40)
+        e2 = float(np.max(np.abs(res.proportions - single.proportions)))
+        ok = ok and e2 <= 1e-5 and res.info["n_iterations"] == 40 and res.h2d_bytes > 0
+        err = max(err, e2)
     tiling.release_communicators()
     flags = torch.tensor([int(ok), halo], device="cuda")
     dist.all_reduce(flags, op=dist.ReduceOp.MIN)
