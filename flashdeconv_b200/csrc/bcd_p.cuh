@@ -365,19 +365,21 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
         const int peer = threadIdx.x;
         unsigned *pc = reinterpret_cast<unsigned *>(comm.peer_base[peer] + comm.comm_off);       // the peer's comm block
         unsigned *slot = pc + kMaxRanks + (parity * kMaxRanks + comm.rank) * 2;
-        __threadfence_system();                      // after every CTA's sweep + pushes (observed through `arrived`)
+        // two plain stores and ONE release: st.release.sys orders them -- and, cumulatively, every CTA's sweep + pushes
+        // this thread observed through `arrived` -- before the flag, without separate system fences (each of those
+        // is a round trip over NVLink)
         slot[0] = *reinterpret_cast<volatile unsigned *>(&state->max_diff_bits);
         slot[1] = *reinterpret_cast<volatile unsigned *>(&state->max_abs_bits);
-        __threadfence_system();
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pc + comm.rank), "r"(comm.seq) : "memory");
         const unsigned *mine = reinterpret_cast<const unsigned *>(comm.peer_base[comm.rank] + comm.comm_off);
         const long long t0 = clock64();
         for (;;) {
             unsigned v;
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + peer) : "memory");
+            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + peer) : "memory");
             if ((int)(v - comm.seq) >= 0 || (comm.debug & 1)) break;
             if (clock64() - t0 > 120000000000LL) { s_timeout = 1; break; }                       // ~60 s: a peer is gone
         }
+        asm volatile("fence.acq_rel.sys;" ::: "memory");          // the peer's rows and norm words are visible from here on
     }
     __syncthreads();
     if (threadIdx.x == 0) {
