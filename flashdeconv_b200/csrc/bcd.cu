@@ -288,6 +288,7 @@ bcd_init_kernel(float *__restrict__ beta, int64_t n_rows, int kp, int n_types, S
     if (i == 0 && state) {
         SolveState z = {};
         z.last_max_abs = n_types > 0 ? 1.0f / (float)n_types : 0.f;      // bound on |beta| for the first sweep (fp16 tile scale)
+        z.ov_new[0] = __float_as_uint(z.last_max_abs);                   // the same bound, overlapped multi-GPU mode
         *state = z;
     }
     if (i >= n_rows * kp) return;

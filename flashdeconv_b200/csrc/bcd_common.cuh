@@ -167,23 +167,34 @@ __device__ __forceinline__ u64 sub2q(const u64 a, const u64 b)
 }
 
 
-// Multi-GPU extension of the production sweep kernel (world <= 1: unused).  The rank's boundary rows -- own rows that a
-// neighbouring tile reads as halo -- are written straight into the peers' beta_out buffers (NVLink peer memory) from
-// the store phase of the patch that produced them; patches holding boundary rows are walked FIRST (patch_order), so the
-// transfers overlap the interior patches.  The last CTA to finish then publishes the rank's two max-norm words and a
-// sweep sequence number into every peer's comm block, waits for theirs, reduces (MAX, core/solver.py:395-397) and runs
-// the stop test: one launch per sweep, no NCCL, no host synchronisation.  (Ordering argument: peer.cu.)
+// Multi-GPU extension of the production sweep kernel (world <= 1: unused).
+//   * The rank's boundary rows -- own rows that a neighbouring tile reads as halo -- are written straight into the
+//     peers' beta_out buffers (NVLink peer memory) from the store phase of the patch that produced them.
+//   * The inter-rank hand-shake (max norms for the stop test, core/solver.py:395-397, and "my rows of the last sweep
+//     are in your halo slots") costs two system-scope round trips plus rank skew -- 10 + 16 us measured on 8 GPUs
+//     against 23 us of compute for a 125k-spot tile.  It is therefore OVERLAPPED: the kernel of sweep t carries the
+//     hand-shake of sweep t - 1 in one dedicated CTA (block 0), the other CTAs walk the INTERIOR patches (no peer
+//     data needed) first, and only the patches that hold boundary rows -- last in the order -- wait for that CTA's
+//     `hs_done` word (and for its verdict: a sweep found converged makes them stop, the speculative interior work is
+//     simply never read).  A peer cannot overwrite halo rows this rank still reads: it pushes sweep t + 1 only after
+//     its own hand-shake of sweep t, which needs this rank's flag, which this rank publishes at the start of its
+//     kernel t + 1 -- after its kernel t has finished (stream order).  One launch per sweep, no NCCL, no host sync.
 constexpr int kMaxRanks = 16;
+constexpr int kCommStatWords = 4;                       // per (parity, rank): max|delta|, max|old|, max|new|, spare
+constexpr int kCommWords = kMaxRanks + 2 * kMaxRanks * kCommStatWords;      // 144 words; the host reserves 256
 struct SweepComm {
-    const int32_t *patch_order;     // [n_patches] processing order, boundary patches first (null: natural order)
-    const int32_t *n_boundary;      // device scalar: how many leading patches of that order hold boundary rows
+    const int32_t *patch_order;     // [n_patches] patches holding boundary rows first (walked backwards: interior first)
+    const int32_t *n_boundary;      // device scalar: how many patches hold boundary rows
     const int32_t *push_ptr;        // [n_rows + 1] push entries of every own row
     const int2 *push_ent;           // (peer, destination row inside the peer's beta buffers)
-    float *peer_base[kMaxRanks];    // symmetric buffers: [beta_a cap_rows*Kp][beta_b cap_rows*Kp][comm words]
+    float *peer_base[kMaxRanks];    // symmetric buffers: [beta_a cap_rows*Kp][beta_b cap_rows*Kp][comm words]...
     long long out_off;              // float offset of beta_out inside a symmetric buffer
     long long comm_off;             // float offset of the comm block
     int rank, world;
-    unsigned seq;                   // sequence number of this sweep
+    unsigned seq;                   // flag value of THIS launch's hand-shake ("sweep `sweep - 1` finished everywhere")
+    int sweep;                      // 1-based index of the sweep this launch computes (max_iter + 1 for the closing launch)
+    int hs_only;                    // closing launch: hand-shake of the last sweep, no patches
+    int finalize_prev;              // the hand-shake closes a sweep (stop test, sweep counter)
     int debug;                      // timing experiments only: bit 0 = do not wait for the peers, bit 1 = do not push rows
 };
 

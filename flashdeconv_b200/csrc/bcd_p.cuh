@@ -50,28 +50,93 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
     uint32_t *g_tile = reinterpret_cast<uint32_t *>(c_tile + TILE * S);           // (TILE + HCAP) x GROW words
     uint8_t *idx_tile = reinterpret_cast<uint8_t *>(g_tile + (TILE + HCAP) * GROW);     // NW x kCodeRounds x 32 byte codes
     int *scal = reinterpret_cast<int *>(idx_tile + NW * kCodeRounds * 32);        // 3 x TILE: row start, end, halo id
-    __shared__ unsigned red[2][NW];
-    __shared__ int s_last;
+    __shared__ unsigned red[3][NW];
+    __shared__ int s_flag;
 
     if (*reinterpret_cast<volatile int *>(&state->converged)) return;      // uniform across the grid (and across ranks)
     // COMM = false (single GPU) compiles the multi-GPU extension out: the loop below is the round-1 kernel unchanged
     const bool comm_on = COMM && comm.world > 1;
-    const int n_push_patches = comm_on ? __ldg(comm.n_boundary) : 0;
-    auto patch_at = [&](int pi) { return (COMM && comm.patch_order) ? __ldg(comm.patch_order + pi) : pi; };
 
-    // Range of the fp16 gather tile.  Every |beta_in| is at most last_max_abs + last_max_diff (max|beta| of the sweep
-    // before plus the largest step it took; fdb_bcd_init seeds 1/K), so with 2^x <= bound < 2^(x+1) the tile stores
+    // ---------------- multi-GPU: block 0 carries the hand-shake of the PREVIOUS sweep and nothing else
+    if (comm_on && blockIdx.x == 0) {
+        const int pp = (comm.sweep + 1) & 1;                                // parity of the sweep being closed
+        const int pn3 = (comm.sweep + 2) % 3;                              // its slot of max|beta_new| ((sweep - 1) mod 3)
+        __shared__ int s_timeout;
+        if (threadIdx.x == 0) s_timeout = 0;
+        __syncthreads();
+        if ((int)threadIdx.x < comm.world) {
+            const int peer = threadIdx.x;
+            unsigned *pc = reinterpret_cast<unsigned *>(comm.peer_base[peer] + comm.comm_off);   // the peer's comm block
+            unsigned *slot = pc + kMaxRanks + (pp * kMaxRanks + comm.rank) * kCommStatWords;
+            // plain stores and ONE release: st.release.sys orders them -- and every write of the previous launches on
+            // this stream (the sweep's pushes) -- before the flag
+            slot[0] = *reinterpret_cast<volatile unsigned *>(&state->ov_diff[pp]);
+            slot[1] = *reinterpret_cast<volatile unsigned *>(&state->ov_abs[pp]);
+            slot[2] = *reinterpret_cast<volatile unsigned *>(&state->ov_new[pn3]);
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pc + comm.rank), "r"(comm.seq) : "memory");
+            const unsigned *mine = reinterpret_cast<const unsigned *>(comm.peer_base[comm.rank] + comm.comm_off);
+            const long long t0 = clock64();
+            for (;;) {
+                unsigned v;
+                asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + peer) : "memory");
+                if ((int)(v - comm.seq) >= 0 || (comm.debug & 1)) break;
+                if (clock64() - t0 > 120000000000LL) { s_timeout = 1; break; }                   // ~60 s: a peer is gone
+            }
+            asm volatile("fence.acq_rel.sys;" ::: "memory");      // the peers' rows and norm words are visible from here on
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (s_timeout) {
+                state->converged = 2;                                                            // surfaced as an error by the host
+            } else {
+                const unsigned *mine = reinterpret_cast<const unsigned *>(comm.peer_base[comm.rank] + comm.comm_off);
+                unsigned md = 0u, ma = 0u, mn = 0u;
+                for (int p = 0; p < comm.world; ++p) {
+                    const volatile unsigned *sl = mine + kMaxRanks + (pp * kMaxRanks + p) * kCommStatWords;
+                    md = max(md, sl[0]);
+                    ma = max(ma, sl[1]);
+                    mn = max(mn, sl[2]);
+                }
+                if (comm.finalize_prev) {
+                    state->max_diff_bits = md;
+                    state->max_abs_bits = ma;
+                    finalize_state(state, tol);
+                }
+                state->last_max_abs = __uint_as_float(mn);        // max over ALL ranks of |beta| after the closed sweep
+                state->last_max_diff = 0.f;
+                state->ov_diff[pp] = 0u;
+                state->ov_abs[pp] = 0u;
+                state->ov_new[(comm.sweep + 1) % 3] = 0u;         // the slot the NEXT sweep accumulates into
+            }
+            __threadfence();
+            *reinterpret_cast<volatile unsigned *>(&state->hs_done) = comm.seq;
+        }
+        return;
+    }
+    const int n_boundary = comm_on ? __ldg(comm.n_boundary) : 0;
+    const int n_workers = comm_on ? (int)gridDim.x - 1 : (int)gridDim.x;
+    const int worker = comm_on ? (int)blockIdx.x - 1 : (int)blockIdx.x;
+    // multi-GPU: the order array lists the boundary patches first; it is walked BACKWARDS (interior patches first)
+    auto patch_at = [&](int pi) { return comm_on ? __ldg(comm.patch_order + (n_patches - 1 - pi)) : pi; };
+    const int first_boundary = n_patches - n_boundary;    // positions >= this hold boundary rows (multi-GPU only)
+
+    // Range of the fp16 gather tile.  With 2^x <= bound < 2^(x+1) on the magnitude of every beta_in the tile stores
     // beta * 2^(8-x): magnitudes below 512, sums of up to 64 neighbours below 32768 < 65504, and values down to
     // 1e-7 of the largest one keep all 11 bits.  Powers of two: results are bit-identical to an unscaled tile whenever
     // that one neither overflows nor underflows.  lam_s folds the factor back in.
+    // Single GPU: bound = last_max_abs + last_max_diff (max|beta| of the sweep before plus its largest step;
+    // fdb_bcd_init seeds 1/K).  Multi-GPU: interior patches gather this rank's rows only, so the rank's own
+    // max|beta_new| of the previous sweep bounds them; boundary patches use the all-rank maximum the hand-shake left
+    // in last_max_abs (they wait for it anyway).
     float inv_s, lam_s;
-    {
-        const float bound = *reinterpret_cast<volatile float *>(&state->last_max_abs) +
-                            *reinterpret_cast<volatile float *>(&state->last_max_diff);
+    auto set_scale = [&](float bound) {
         const int ef = min(max((int)((__float_as_uint(bound) >> 23) & 255u), 9), 245);
         inv_s = __uint_as_float((unsigned)(262 - ef) << 23);
         lam_s = lam * __uint_as_float((unsigned)(ef - 8) << 23);
-    }
+    };
+    if (comm_on) set_scale(__uint_as_float(*reinterpret_cast<volatile unsigned *>(&state->ov_new[(comm.sweep + 2) % 3])));
+    else set_scale(*reinterpret_cast<volatile float *>(&state->last_max_abs) +
+                   *reinterpret_cast<volatile float *>(&state->last_max_diff));
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wrow = warp * 32;
@@ -105,17 +170,36 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
     };
 
     // ---------------- prologue: the first patch's scalars
-    int pi = blockIdx.x;                                  // position in the processing order
+    int pi = worker;                                      // position in the processing order
     int patch = pi < n_patches ? patch_at(pi) : n_patches;
     if (patch < n_patches) scalars_async(patch);
     asm volatile("cp.async.commit_group;");
     asm volatile("cp.async.wait_all;");
 
-    float dmax = 0.f, amax = 0.f;
+    float dmax = 0.f, amax = 0.f, nmax = 0.f;
+    bool waited = false;
 #pragma unroll 1
-    for (; pi < n_patches; pi += gridDim.x) {
+    for (; pi < n_patches; pi += n_workers) {
+        if (COMM && comm_on && pi >= first_boundary && !waited) {
+            // first patch with boundary rows: the hand-shake of the previous sweep has to be complete (peers' rows of
+            // that sweep are in the halo slots; its stop test decides whether this sweep exists at all)
+            if (threadIdx.x == 0) {
+                const long long t0 = clock64();
+                while (*reinterpret_cast<volatile unsigned *>(&state->hs_done) != comm.seq &&
+                       !*reinterpret_cast<volatile int *>(&state->converged)) {
+                    if (clock64() - t0 > 130000000000LL) { state->converged = 2; break; }       // the hand-shake never came
+                    __nanosleep(200);
+                }
+                __threadfence();
+                s_flag = *reinterpret_cast<volatile int *>(&state->converged);
+            }
+            __syncthreads();
+            if (s_flag) break;                             // the previous sweep converged (or a peer is gone): stop here
+            set_scale(*reinterpret_cast<volatile float *>(&state->last_max_abs));
+            waited = true;
+        }
         const int tile_base = patch * TILE;
-        const int next = pi + (int)gridDim.x < n_patches ? patch_at(pi + gridDim.x) : n_patches;
+        const int next = pi + n_workers < n_patches ? patch_at(pi + n_workers) : n_patches;
         const int my_row = tile_base + own;
         const int my_s = scal[threadIdx.x], my_e = scal[TILE + threadIdx.x];
         const int halo_id = scal[2 * TILE + threadIdx.x];
@@ -295,10 +379,12 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
                     unpack2(add2q(a0, a1), p0, p1);
                     p0 = fmaf(G.cross[k0], b[k0 + 1], p0);
                     const float nv0 = fmaxf(0.f, p0 * ri0);
+                    if (COMM) nmax = fmaxf(nmax, nv0);
                     dm = fmaxf(dm, fabsf(nv0 - b[k0]));
                     b[k0] = nv0;
                     p1 = fmaf(G.cross[k0 + 1], nv0, p1);
                     const float nv1 = fmaxf(0.f, p1 * ri1);
+                    if (COMM) nmax = fmaxf(nmax, nv1);
                     dm = fmaxf(dm, fabsf(nv1 - b[k0 + 1]));
                     b[k0 + 1] = nv1;
                 });
@@ -317,7 +403,7 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
             if (p < n_rows) st4(beta_out + (size_t)p * KP + 4 * q, ld4(c_tile + L::at(wrow + lr, q)));
         }
         // ---------------- boundary rows -> the neighbouring tiles' halo slots (peer memory), from registers
-        if (COMM && pi < n_push_patches && my_row < n_rows && !(comm.debug & 2)) {
+        if (COMM && comm_on && pi >= first_boundary && my_row < n_rows && !(comm.debug & 2)) {
             const int pe = __ldg(comm.push_ptr + my_row + 1);
             for (int u = __ldg(comm.push_ptr + my_row); u < pe; ++u) {
                 const int2 ent = __ldg(comm.push_ent + u);
@@ -335,67 +421,30 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
 
     const unsigned wd = __reduce_max_sync(kFull, __float_as_uint(dmax));
     const unsigned wa = __reduce_max_sync(kFull, __float_as_uint(amax));
-    if (lane == 0) { red[0][warp] = wd; red[1][warp] = wa; }
+    const unsigned wn = COMM ? __reduce_max_sync(kFull, __float_as_uint(nmax)) : 0u;
+    if (lane == 0) { red[0][warp] = wd; red[1][warp] = wa; red[2][warp] = wn; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned bd = 0u, ba = 0u;
+        unsigned bd = 0u, ba = 0u, bn = 0u;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) { bd = max(bd, red[0][w]); ba = max(ba, red[1][w]); }
+        for (int w = 0; w < NW; ++w) { bd = max(bd, red[0][w]); ba = max(ba, red[1][w]); bn = max(bn, red[2][w]); }
+        if (comm_on) {
+            // overlapped mode: this sweep's norms go to their parity slot; the NEXT launch's hand-shake block closes the sweep
+            const int p = comm.sweep & 1;
+            if (bd > *reinterpret_cast<volatile unsigned *>(&state->ov_diff[p])) atomicMax(&state->ov_diff[p], bd);
+            if (ba > *reinterpret_cast<volatile unsigned *>(&state->ov_abs[p])) atomicMax(&state->ov_abs[p], ba);
+            if (bn > *reinterpret_cast<volatile unsigned *>(&state->ov_new[comm.sweep % 3])) atomicMax(&state->ov_new[comm.sweep % 3], bn);
+            return;
+        }
         if (bd > *reinterpret_cast<volatile unsigned *>(&state->max_diff_bits)) atomicMax(&state->max_diff_bits, bd);
         if (ba > *reinterpret_cast<volatile unsigned *>(&state->max_abs_bits)) atomicMax(&state->max_abs_bits, ba);
-        s_last = 0;
         if (finalize) {
-            if (comm_on) __threadfence_system(); else __threadfence();
+            __threadfence();
             if (atomicAdd(&state->arrived, 1u) == gridDim.x - 1) {
                 __threadfence();
-                if (comm_on) s_last = 1;
-                else finalize_state(state, tol);
+                finalize_state(state, tol);
             }
         }
-    }
-    if (!(finalize && comm_on)) return;
-    // ---------------- multi-GPU: the last CTA exchanges max norms + sequence flags with every peer, then finalises
-    __syncthreads();
-    if (!s_last) return;
-    __shared__ int s_timeout;
-    if (threadIdx.x == 0) s_timeout = 0;
-    __syncthreads();
-    const int parity = (int)(comm.seq & 1u);
-    if ((int)threadIdx.x < comm.world) {
-        const int peer = threadIdx.x;
-        unsigned *pc = reinterpret_cast<unsigned *>(comm.peer_base[peer] + comm.comm_off);       // the peer's comm block
-        unsigned *slot = pc + kMaxRanks + (parity * kMaxRanks + comm.rank) * 2;
-        // two plain stores and ONE release: st.release.sys orders them -- and, cumulatively, every CTA's sweep + pushes
-        // this thread observed through `arrived` -- before the flag, without separate system fences (each of those
-        // is a round trip over NVLink)
-        slot[0] = *reinterpret_cast<volatile unsigned *>(&state->max_diff_bits);
-        slot[1] = *reinterpret_cast<volatile unsigned *>(&state->max_abs_bits);
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pc + comm.rank), "r"(comm.seq) : "memory");
-        const unsigned *mine = reinterpret_cast<const unsigned *>(comm.peer_base[comm.rank] + comm.comm_off);
-        const long long t0 = clock64();
-        for (;;) {
-            unsigned v;
-            asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + peer) : "memory");
-            if ((int)(v - comm.seq) >= 0 || (comm.debug & 1)) break;
-            if (clock64() - t0 > 120000000000LL) { s_timeout = 1; break; }                       // ~60 s: a peer is gone
-        }
-        asm volatile("fence.acq_rel.sys;" ::: "memory");          // the peer's rows and norm words are visible from here on
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (s_timeout) { state->converged = 2; state->arrived = 0u; return; }                    // surfaced as an error by the host
-        const unsigned *mine = reinterpret_cast<const unsigned *>(comm.peer_base[comm.rank] + comm.comm_off);
-        unsigned md = 0u, ma = 0u;
-        for (int p = 0; p < comm.world; ++p) {
-            unsigned a, c;
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(a) : "l"(mine + kMaxRanks + (parity * kMaxRanks + p) * 2) : "memory");
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(c) : "l"(mine + kMaxRanks + (parity * kMaxRanks + p) * 2 + 1) : "memory");
-            md = max(md, a);
-            ma = max(ma, c);
-        }
-        state->max_diff_bits = md;
-        state->max_abs_bits = ma;
-        finalize_state(state, tol);
     }
 }
 
@@ -429,7 +478,7 @@ int launch_sweep_p(const float *h, const GramArg<KP> &G, int n_types, const floa
         cm = SweepComm();
         cm.patch_order = nullptr; cm.n_boundary = nullptr; cm.push_ptr = nullptr; cm.push_ent = nullptr;
         for (int p = 0; p < kMaxRanks; ++p) cm.peer_base[p] = nullptr;
-        cm.out_off = cm.comm_off = 0; cm.rank = 0; cm.world = 1; cm.seq = 0u; cm.debug = 0;
+        cm.out_off = cm.comm_off = 0; cm.rank = 0; cm.world = 1; cm.seq = 0u; cm.sweep = 1; cm.hs_only = 0; cm.finalize_prev = 0; cm.debug = 0;
     }
     auto run_p = [&](auto kern) -> int {
         int resident = 0;
@@ -442,9 +491,14 @@ int launch_sweep_p(const float *h, const GramArg<KP> &G, int n_types, const floa
         // is barely more than one round: 977 patches on 888 slots at 8 GPUs)
         const int64_t slots = (int64_t)kNumSM * std::max(resident, 1);
         const int64_t rounds = std::max<int64_t>(ceil_div(n_ctas, slots), 1);
-        const int grid = (int)std::min<int64_t>(std::min<int64_t>(n_ctas, cap), ceil_div(n_ctas, rounds));
+        int grid = (int)std::min<int64_t>(std::min<int64_t>(n_ctas, cap), ceil_div(n_ctas, rounds));
+        if (comm != nullptr) {                              // block 0 = hand-shake; the workers leave it a slot
+            const int64_t wslots = std::max<int64_t>(slots - 1, 1);
+            const int64_t wrounds = std::max<int64_t>(ceil_div(n_ctas, wslots), 1);
+            grid = 1 + (cm.hs_only ? 0 : (int)std::min<int64_t>(std::min<int64_t>(n_ctas, cap), ceil_div(n_ctas, wrounds)));
+        }
         kern<<<grid, tile, smem, st>>>(h, P, beta_in, beta_out, indptr, indices, pv, (int)n_rows, n_types, lam, rho, tol,
-                                       finalize, state, (int)n_ctas, cm);
+                                       finalize, state, cm.hs_only ? 0 : (int)n_ctas, cm);
         FDB_LAUNCH_CHECK("bcd_sweep_p_kernel");
         return FDB_OK;
     };

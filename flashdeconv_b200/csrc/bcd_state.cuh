@@ -13,7 +13,13 @@ struct SolveState {                 // mirrors the 64-byte block documented in f
     float rel_change;
     float last_max_diff;
     float last_max_abs;
-    int pad[8];
+    // overlapped multi-GPU mode (bcd_p.cuh, SweepComm): sweep t accumulates its max norms into slot t & 1 while the
+    // hand-shake of sweep t - 1 consumes the other one; max|beta_new| of this rank rotates over three slots because
+    // sweep t + 1 still reads the value of sweep t (range of its fp16 tile) while the hand-shake of t - 1 recycles one
+    unsigned ov_diff[2];
+    unsigned ov_abs[2];
+    unsigned ov_new[3];
+    unsigned hs_done;               // sequence number of the last completed hand-shake
 };
 static_assert(sizeof(SolveState) == 64, "state block is 64 bytes");
 

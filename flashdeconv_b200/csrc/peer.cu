@@ -18,7 +18,7 @@
 // before flag t+1.  The statistics slots are double-buffered by sweep parity for the same reason.
 //
 // Symmetric buffer layout (floats): [beta_a: cap_rows*Kp][beta_b: cap_rows*Kp][comm: kCommWords u32]
-//   comm: flags[kMaxRanks], stats[2][kMaxRanks][2]
+//   comm: flags[kMaxRanks], stats[2][kMaxRanks][kCommStatWords]
 #include "bcd_common.cuh"
 
 extern "C" int fdb_bcd_sweep(const float *h, const float *host_gram, const float *beta_in, float *beta_out,
@@ -34,7 +34,6 @@ int sweep_with_comm(const float *h, const float *host_gram, const float *beta_in
                     const int32_t *indices, int64_t n_rows, int32_t n_types, float lam, float rho, float tol, void *state,
                     const void *plan, void *stream, const SweepComm &comm);
 
-constexpr int kCommWords = kMaxRanks + 2 * kMaxRanks * 2;      // 80 words; the host reserves 256
 
 struct PeerBases {
     float *base[kMaxRanks];
@@ -82,7 +81,7 @@ peer_sync_kernel(SolveState *st, PeerBases pb, int64_t comm_off, int rank, int w
     __syncthreads();
     if (peer < world) {
         unsigned *pc = reinterpret_cast<unsigned *>(pb.base[peer] + comm_off);       // the peer's comm block
-        unsigned *slot = pc + kMaxRanks + (parity * kMaxRanks + rank) * 2;
+        unsigned *slot = pc + kMaxRanks + (parity * kMaxRanks + rank) * kCommStatWords;
         __threadfence_system();                      // order after this rank's sweep + push (earlier kernels)
         slot[0] = st->max_diff_bits;
         slot[1] = st->max_abs_bits;
@@ -101,8 +100,8 @@ peer_sync_kernel(SolveState *st, PeerBases pb, int64_t comm_off, int rank, int w
         const unsigned *mine = reinterpret_cast<const unsigned *>(pb.base[rank] + comm_off);
         unsigned md = 0u, ma = 0u;
         for (int p = 0; p < world; ++p) {
-            md = max(md, ld_acquire_sys(mine + kMaxRanks + (parity * kMaxRanks + p) * 2));
-            ma = max(ma, ld_acquire_sys(mine + kMaxRanks + (parity * kMaxRanks + p) * 2 + 1));
+            md = max(md, ld_acquire_sys(mine + kMaxRanks + (parity * kMaxRanks + p) * kCommStatWords));
+            ma = max(ma, ld_acquire_sys(mine + kMaxRanks + (parity * kMaxRanks + p) * kCommStatWords + 1));
         }
         st->max_diff_bits = md;
         st->max_abs_bits = ma;
@@ -155,31 +154,41 @@ FDB_API int fdb_bcd_solve_peer(const float *h, const float *host_gram, void *con
     cm.comm_off = off_comm;
     cm.rank = rank;
     cm.world = world;
-    cm.debug = getenv("FDB_PEER_DEBUG") ? atoi(getenv("FDB_PEER_DEBUG")) : 0;
+    cm.debug = 0;
     int64_t cur = off_a, nxt = off_b;
     const int chunks = kp / 4;
-    for (int it = 0; it < max_iter; ++it) {
-        const unsigned seq = seq_base + (unsigned)it + 1u;
-        if (fused && n_boundary != nullptr) {
+    if (fused && n_boundary != nullptr) {
+        // overlapped form: launch t computes sweep t and carries the hand-shake that closes sweep t - 1 (block 0); a closing
+        // launch does the hand-shake of the last sweep.  Flag value of launch t: seq_base + t.
+        cm.debug = getenv("FDB_PEER_DEBUG") ? atoi(getenv("FDB_PEER_DEBUG")) : 0;
+        for (int it = 1; it <= max_iter + 1; ++it) {
             cm.out_off = nxt;
-            cm.seq = seq;
+            cm.seq = seq_base + (unsigned)it;
+            cm.sweep = it;
+            cm.hs_only = it == max_iter + 1;
+            cm.finalize_prev = it > 1;
+            if (cm.hs_only && max_iter == 0) break;
             rc = sweep_with_comm(h, host_gram, mine + cur, mine + nxt, indptr, indices, n_own, n_types, lambda, rho_scaled,
                                  tol, state, plan, stream, cm);
             if (rc) return rc;
-        } else {
-            if (n_own > 0) {
-                rc = fdb_bcd_sweep(h, host_gram, mine + cur, mine + nxt, indptr, indices, n_own, n_types, lambda,
-                                   rho_scaled, tol, 0, state, plan, stream);
-                if (rc) return rc;
-                if (world > 1) {
-                    peer_push_kernel<<<(int)ceil_div(n_own * chunks, 256), 256, 0, st>>>(
-                        mine + nxt, pb, nxt, push_ptr, (const int2 *)push_ent, n_own, chunks, (const SolveState *)state);
-                    FDB_LAUNCH_CHECK("peer_push_kernel");
-                }
-            }
-            peer_sync_kernel<<<1, kMaxRanks, 0, st>>>((SolveState *)state, pb, off_comm, rank, world, seq, tol, 1);
-            FDB_LAUNCH_CHECK("peer_sync_kernel");
+            const int64_t t = cur; cur = nxt; nxt = t;
         }
+        return FDB_OK;
+    }
+    for (int it = 0; it < max_iter; ++it) {
+        const unsigned seq = seq_base + (unsigned)it + 1u;
+        if (n_own > 0) {
+            rc = fdb_bcd_sweep(h, host_gram, mine + cur, mine + nxt, indptr, indices, n_own, n_types, lambda,
+                               rho_scaled, tol, 0, state, plan, stream);
+            if (rc) return rc;
+            if (world > 1) {
+                peer_push_kernel<<<(int)ceil_div(n_own * chunks, 256), 256, 0, st>>>(
+                    mine + nxt, pb, nxt, push_ptr, (const int2 *)push_ent, n_own, chunks, (const SolveState *)state);
+                FDB_LAUNCH_CHECK("peer_push_kernel");
+            }
+        }
+        peer_sync_kernel<<<1, kMaxRanks, 0, st>>>((SolveState *)state, pb, off_comm, rank, world, seq, tol, 1);
+        FDB_LAUNCH_CHECK("peer_sync_kernel");
         const int64_t t = cur; cur = nxt; nxt = t;
     }
     return FDB_OK;
