@@ -32,6 +32,8 @@ SIGNATURES = {
     "fdb_graph_workspace_bytes": (_i64, [_i64, _i32]),
     "fdb_graph_build": (C.c_int, [_vp, _i64, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _i64,
                                   C.POINTER(_i64), C.POINTER(_f64), _vp, _i64, _vp]),
+    "fdb_graph_build_nd": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _f64, _vp, _vp, _vp, _vp, _i64,
+                                     C.POINTER(_i64), C.POINTER(_f64), _vp, _i64, _vp]),
     "fdb_graph_to_input_order": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
     "fdb_bcd_init": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "fdb_bcd_sweep": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _f32, _i32, _vp, _vp, _vp]),
@@ -42,6 +44,8 @@ SIGNATURES = {
     "fdb_objective_terms": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "fdb_finish": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "fdb_gene_moments_csr": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "fdb_dominant_type": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "fdb_group_sums_csr": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "fdb_rows_gather": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),
     "fdb_peer_comm_floats": (_i64, []),
     "fdb_bcd_solve_peer": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i64, _vp, _vp, _i64, _i64, _i32, _f32, _f32, _i32, _f32,

@@ -501,6 +501,24 @@ finish_kernel(const float *__restrict__ beta, const int32_t *__restrict__ order,
     }
 }
 
+// dominant cell type per spot (FlashDeconv.get_dominant_cell_type, core/deconv.py:467-478): argmax over the K abundances,
+// first maximum on ties like numpy.argmax; equal to the argmax of the proportions (a positive row scaling), 0 for all-zero rows
+__global__ void __launch_bounds__(256)
+dominant_kernel(const float *__restrict__ beta, const int32_t *__restrict__ order, int64_t n_rows, int kp, int n_types,
+                int32_t *__restrict__ out)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_rows) return;
+    const float *row = beta + p * kp;
+    float best = row[0];
+    int arg = 0;
+    for (int k = 1; k < n_types; ++k) {
+        const float v = row[k];
+        if (v > best) { best = v; arg = k; }
+    }
+    out[order ? (int64_t)order[p] : p] = arg;
+}
+
 __global__ void __launch_bounds__(256)
 rows_gather_kernel(const float *__restrict__ src, const int32_t *__restrict__ rows, int64_t n_list,
                    int chunks, float *__restrict__ dst)
@@ -660,6 +678,18 @@ extern "C" __attribute__((visibility("default"))) int fdb_finish(const float *be
     finish_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(beta, order, n_rows, fdb_padded_types(n_types), n_types,
                                                          beta_out, prop_out);
     FDB_LAUNCH_CHECK("finish_kernel");
+    return FDB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fdb_dominant_type(const float *beta, const int32_t *order, int64_t n_rows, int32_t n_types,
+                                 int32_t *dominant, void *stream)
+{
+    FDB_REQUIRE(n_rows >= 0 && n_types >= 1 && n_types <= FDB_MAX_TYPES, "bad shape");
+    if (n_rows == 0) return FDB_OK;
+    FDB_REQUIRE(beta && dominant, "null pointer");
+    dominant_kernel<<<(int)ceil_div(n_rows, 256), 256, 0, (cudaStream_t)stream>>>(beta, order, n_rows, fdb_padded_types(n_types),
+                                                                               n_types, dominant);
+    FDB_LAUNCH_CHECK("dominant_kernel");
     return FDB_OK;
 }
 

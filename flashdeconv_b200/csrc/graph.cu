@@ -337,6 +337,169 @@ knn_kernel(const double2 *__restrict__ xy, const int32_t *__restrict__ order, in
     }
 }
 
+// ---------------------------------------------------------------- general path: any dimension D <= 3, any k
+// utils/graph.py:15-22 accepts coords with D >= 1 columns and any k.  The grid-hash kernels above are 2-D with the k
+// best candidates in registers (k <= 32); everything else -- 1-D / 3-D coordinates, k > 32 -- goes through exhaustive
+// search in tile order (N^2 / 2 distance evaluations in float64: exact, ~5 ms at 100k spots, a fallback by design).
+// Tile order comes from the first two coordinates (any permutation is valid; it only has to be spatially coherent).
+struct double3p { double x, y, z; };
+
+__global__ void __launch_bounds__(256)
+project_xy_kernel(const double *__restrict__ coords, int64_t n, int dims, double *__restrict__ xy)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    xy[2 * i] = coords[i * dims];
+    xy[2 * i + 1] = dims > 1 ? coords[i * dims + 1] : 0.0;
+}
+__global__ void __launch_bounds__(256)
+gather_nd_kernel(const double *__restrict__ coords, const int32_t *__restrict__ order, int64_t n, int dims,
+                 double3p *__restrict__ sorted)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int64_t o = order[p];
+    double3p c;
+    c.x = coords[o * dims];
+    c.y = dims > 1 ? coords[o * dims + 1] : 0.0;
+    c.z = dims > 2 ? coords[o * dims + 2] : 0.0;
+    sorted[p] = c;
+}
+__device__ __forceinline__ double dist2_nd(const double3p &a, const double3p &b)
+{
+    const double dx = __dsub_rn(a.x, b.x), dy = __dsub_rn(a.y, b.y), dz = __dsub_rn(a.z, b.z);
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));     // no FMA contraction
+}
+
+constexpr int kBruteTile = 256;
+template <int KB>
+__global__ void __launch_bounds__(128)
+knn_brute_kernel(const double3p *__restrict__ pts, const int32_t *__restrict__ order, int64_t n, int k,
+                 int32_t *__restrict__ knn, double *__restrict__ kth_dist)
+{
+    __shared__ double3p tile[kBruteTile];
+    __shared__ int32_t tile_o[kBruteTile];
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = p < n;
+    const double3p me = pts[live ? p : 0];
+    double bd[KB];
+    int bi[KB], bo[KB];                                   // candidate position, its original index (tie order)
+    for (int i = 0; i < k; ++i) { bd[i] = INFINITY; bi[i] = -1; bo[i] = 0x7fffffff; }
+    for (int64_t base = 0; base < n; base += kBruteTile) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < kBruteTile; t += blockDim.x)
+            if (base + t < n) { tile[t] = pts[base + t]; tile_o[t] = order[base + t]; }
+        __syncthreads();
+        if (!live) continue;
+        const int m = (int)min((int64_t)kBruteTile, n - base);
+        for (int t = 0; t < m; ++t) {
+            const int64_t q = base + t;
+            if (q == p) continue;
+            const double d2 = dist2_nd(me, tile[t]);
+            const int oq = tile_o[t];
+            if (d2 > bd[k - 1] || (d2 == bd[k - 1] && oq > bo[k - 1])) continue;
+            int i = k - 1;                                // insertion keeps (distance, original index) ascending
+            while (i > 0 && (bd[i - 1] > d2 || (bd[i - 1] == d2 && bo[i - 1] > oq))) {
+                bd[i] = bd[i - 1]; bi[i] = bi[i - 1]; bo[i] = bo[i - 1];
+                --i;
+            }
+            bd[i] = d2; bi[i] = (int)q; bo[i] = oq;
+        }
+    }
+    if (!live) return;
+    for (int i = 0; i < k; ++i) knn[p * k + i] = bi[i];
+    if (kth_dist) kth_dist[p] = sqrt(bd[k - 1]);
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128)
+radius_brute_kernel(const double3p *__restrict__ pts, int64_t n, double r2, int32_t *__restrict__ deg,
+                    const int32_t *__restrict__ indptr, int32_t *__restrict__ indices)
+{
+    __shared__ double3p tile[kBruteTile];
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = p < n;
+    const double3p me = pts[live ? p : 0];
+    int cnt = 0;
+    const int base_out = (FILL && live) ? indptr[p] : 0;
+    for (int64_t base = 0; base < n; base += kBruteTile) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < kBruteTile; t += blockDim.x)
+            if (base + t < n) tile[t] = pts[base + t];
+        __syncthreads();
+        if (!live) continue;
+        const int m = (int)min((int64_t)kBruteTile, n - base);
+        for (int t = 0; t < m; ++t) {
+            if (base + t == p) continue;
+            if (dist2_nd(me, tile[t]) <= r2) {
+                if (FILL) indices[base_out + cnt] = (int32_t)(base + t);
+                ++cnt;
+            }
+        }
+    }
+    if (!FILL && live) deg[p] = cnt;
+}
+
+// ---------------------------------------------------------------- order statistics on the device (radix select)
+// Non-negative doubles order like their bit patterns.  Eight passes of 8 bits from the top: a histogram of the
+// current byte over the keys that match the prefix found so far, then one thread walks the 256 bins.  No host sync.
+struct SelectState {
+    unsigned long long prefix;      // key bits decided so far (high bytes)
+    long long rank;                 // rank of the wanted element among the keys matching the prefix
+    unsigned hist[256];
+};
+__global__ void select_init_kernel(SelectState *st, long long rank)
+{
+    st->prefix = 0ull;
+    st->rank = rank;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) st->hist[i] = 0u;
+}
+__global__ void __launch_bounds__(256)
+select_hist_kernel(const double *__restrict__ v, int64_t n, int pass, SelectState *st)
+{
+    __shared__ unsigned sh[256];
+    sh[threadIdx.x] = 0u;
+    __syncthreads();
+    const int shift = 56 - 8 * pass;
+    const unsigned long long prefix = st->prefix;
+    const unsigned long long mask = pass == 0 ? 0ull : ~0ull << (shift + 8);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long key = (unsigned long long)__double_as_longlong(v[i]);
+        if ((key & mask) == prefix) atomicAdd(&sh[(key >> shift) & 255ull], 1u);
+    }
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], sh[threadIdx.x]);
+}
+__global__ void select_pick_kernel(SelectState *st, int pass, double *out)
+{
+    if (threadIdx.x == 0) {
+        long long r = st->rank;
+        int b = 0;
+        for (; b < 255; ++b) {
+            if (r < (long long)st->hist[b]) break;
+            r -= st->hist[b];
+        }
+        st->rank = r;
+        st->prefix |= (unsigned long long)b << (56 - 8 * pass);
+        if (pass == 7) *out = __longlong_as_double((long long)st->prefix);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) st->hist[i] = 0u;
+}
+// out[0] <- the element of rank `rank` (0-based, ascending) of v[0..n), all values >= 0
+static int device_select(const double *v, int64_t n, long long rank, SelectState *st, double *out, cudaStream_t stream)
+{
+    select_init_kernel<<<1, 256, 0, stream>>>(st, rank);
+    const int blocks = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)kNumSM * 8);
+    for (int pass = 0; pass < 8; ++pass) {
+        select_hist_kernel<<<blocks, 256, 0, stream>>>(v, n, pass, st);
+        select_pick_kernel<<<1, 256, 0, stream>>>(st, pass, out);
+    }
+    count_launches(16);
+    FDB_LAUNCH_CHECK("device_select");
+    return FDB_OK;
+}
+
 // ---------------------------------------------------------------- symmetrise the directed kNN lists
 __global__ void __launch_bounds__(256)
 reverse_count_kernel(const int32_t *__restrict__ knn, int64_t n, int k, int32_t *__restrict__ extra)
@@ -483,6 +646,10 @@ struct GraphScratch {
     int32_t *cell_of, *hist, *cursor, *tile_rank, *block_sums, *knn, *extra, *deg;
     double2 *xy;
     double *kth;
+    double *xy_proj;                 // general path: first two coordinates of every spot (input order)
+    double3p *pts;                   // general path: coordinates in tile order, padded to three
+    SelectState *select;
+    double *select_out;              // two order statistics
     int64_t bytes;
 };
 
@@ -504,6 +671,10 @@ static GraphScratch carve(void *ws, int64_t n, int k)
     s.deg = b.take<int32_t>(n + 1);
     s.xy = b.take<double2>(n);
     s.kth = b.take<double>(n);
+    s.xy_proj = b.take<double>(2 * n);
+    s.pts = b.take<double3p>(n);
+    s.select = b.take<SelectState>(1);
+    s.select_out = b.take<double>(2);
     s.bytes = round_up(b.off, 256);
     return s;
 }
@@ -593,15 +764,22 @@ static void launch_knn(const GraphScratch &s, const int32_t *order, int64_t n, c
 }
 
 static int run_knn(const GraphScratch &s, const int32_t *order, int64_t n, const GridSpec &g, int k,
-                   double *kth, cudaStream_t st)
+                   double *kth, cudaStream_t st, bool general)
 {
+    if (general || k > 32) {                    // exhaustive search: any dimension, any k <= 1024
+        if (k <= 32) knn_brute_kernel<32><<<grid1d(n, 128), 128, 0, st>>>(s.pts, order, n, k, s.knn, kth);
+        else if (k <= 128) knn_brute_kernel<128><<<grid1d(n, 128), 128, 0, st>>>(s.pts, order, n, k, s.knn, kth);
+        else if (k <= 1024) knn_brute_kernel<1024><<<grid1d(n, 128), 128, 0, st>>>(s.pts, order, n, k, s.knn, kth);
+        else {
+            set_error("k_neighbors > 1024 is not supported (got %d)", k);
+            return FDB_ERR_UNSUPPORTED;
+        }
+        FDB_LAUNCH_CHECK("knn_brute_kernel");
+        return FDB_OK;
+    }
     if (k <= 8) launch_knn<8>(s, order, n, g, k, kth, st);
     else if (k <= 16) launch_knn<16>(s, order, n, g, k, kth, st);
-    else if (k <= 32) launch_knn<32>(s, order, n, g, k, kth, st);
-    else {
-        set_error("k_neighbors > 32 is not supported by the register-resident kNN kernel (got %d)", k);
-        return FDB_ERR_UNSUPPORTED;
-    }
+    else launch_knn<32>(s, order, n, g, k, kth, st);
     FDB_LAUNCH_CHECK("knn_kernel");
     return FDB_OK;
 }
@@ -616,13 +794,14 @@ extern "C" __attribute__((visibility("default"))) int64_t fdb_graph_workspace_by
     return carve(nullptr, n_spots, k).bytes;
 }
 
-extern "C" __attribute__((visibility("default"))) int fdb_graph_build(const double *coords, int64_t n, int32_t mode, int32_t k, double radius,
-                               int32_t *order, int32_t *rank, int32_t *indptr, int32_t *indices,
+extern "C" __attribute__((visibility("default"))) int fdb_graph_build_nd(const double *coords_nd, int64_t n, int32_t dims, int32_t mode, int32_t k,
+                               double radius, int32_t *order, int32_t *rank, int32_t *indptr, int32_t *indices,
                                int64_t indices_capacity, int64_t *host_nnz, double *host_radius,
                                void *workspace, int64_t workspace_bytes, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     FDB_REQUIRE(n >= 0 && n < (int64_t)1 << 31, "n_spots out of range");
+    FDB_REQUIRE(dims >= 1 && dims <= 3, "coords must have 1, 2 or 3 columns, got %d", dims);
     FDB_REQUIRE(mode >= 0 && mode <= 2, "unknown graph mode %d", mode);
     FDB_REQUIRE(host_nnz != nullptr, "host_nnz is required");
     FDB_REQUIRE(mode != 0 || k >= 0, "k_neighbors must be non-negative, got %d", k);
@@ -636,7 +815,15 @@ extern "C" __attribute__((visibility("default"))) int fdb_graph_build(const doub
         set_error("graph workspace too small: need %lld bytes, got %lld", (long long)s.bytes, (long long)workspace_bytes);
         return FDB_ERR_WORKSPACE;
     }
-    FDB_REQUIRE(coords && order && rank && indptr, "null pointer");
+    FDB_REQUIRE(coords_nd && order && rank && indptr, "null pointer");
+    // general path (exhaustive search in tile order): anything but 2-D coordinates with k <= 32
+    const bool general = dims != 2 || (mode == 0 && k_eff > 32);
+    const double *coords = coords_nd;
+    if (dims != 2) {                             // tile order from the first two coordinates
+        project_xy_kernel<<<grid1d(n, 256), 256, 0, st>>>(coords_nd, n, dims, s.xy_proj);
+        FDB_LAUNCH_CHECK("project_xy_kernel");
+        coords = s.xy_proj;
+    }
 
     // bounding box (one host sync)
     const int bb_blocks = (int)std::min<int64_t>(1024, ceil_div(n, 256));
@@ -654,9 +841,13 @@ extern "C" __attribute__((visibility("default"))) int fdb_graph_build(const doub
                 "coords contain non-finite values");
 
     std::vector<int32_t> tile_rank;
-    GridSpec g = make_grid(lo_x, lo_y, hi_x, hi_y, n, mode == 1 ? radius : 0.0, tile_rank);
+    GridSpec g = make_grid(lo_x, lo_y, hi_x, hi_y, n, (mode == 1 && !general) ? radius : 0.0, tile_rank);
     int rc = bin_spots(coords, n, g, tile_rank, s, order, rank, st);
     if (rc) return rc;
+    if (general) {
+        gather_nd_kernel<<<grid1d(n, 256), 256, 0, st>>>(coords_nd, order, n, dims, s.pts);
+        FDB_LAUNCH_CHECK("gather_nd_kernel");
+    }
 
     if (mode == 2) {
         // radius = 1.5 * median nearest-neighbour distance (utils/graph.py:163-170)
@@ -664,22 +855,23 @@ extern "C" __attribute__((visibility("default"))) int fdb_graph_build(const doub
             FDB_CUDA(cudaMemsetAsync(indptr, 0, (n + 1) * 4, st));
             return FDB_OK;
         }
-        rc = run_knn(s, order, n, g, 1, s.kth, st);
+        rc = run_knn(s, order, n, g, 1, s.kth, st, general);
         if (rc) return rc;
-        std::vector<double> d1(n);
-        FDB_CUDA(cudaMemcpyAsync(d1.data(), s.kth, n * 8, cudaMemcpyDeviceToHost, st));
-        FDB_CUDA(cudaStreamSynchronize(st));
-        // numpy median: mean of the two middle order statistics for even n
+        // numpy median on the device: the middle order statistic, or the mean of the two middle ones for even n
         const int64_t mid = n / 2;
-        std::nth_element(d1.begin(), d1.begin() + mid, d1.end());
-        double med = d1[mid];
+        rc = device_select(s.kth, n, mid, s.select, s.select_out, st);
+        if (rc) return rc;
         if (n % 2 == 0) {
-            const double below = *std::max_element(d1.begin(), d1.begin() + mid);
-            med = (below + med) / 2.0;          // numpy: mean of the two middle values
+            rc = device_select(s.kth, n, mid - 1, s.select, s.select_out + 1, st);
+            if (rc) return rc;
         }
+        double med2[2] = {0.0, 0.0};
+        FDB_CUDA(cudaMemcpyAsync(med2, s.select_out, 16, cudaMemcpyDeviceToHost, st));
+        FDB_CUDA(cudaStreamSynchronize(st));
+        const double med = n % 2 == 0 ? (med2[1] + med2[0]) / 2.0 : med2[0];
         radius = med * 1.5;
         if (host_radius) *host_radius = radius;
-        if (radius > g.cell) {                   // re-bin with cells at least `radius` wide
+        if (!general && radius > g.cell) {       // re-bin with cells at least `radius` wide
             g = make_grid(lo_x, lo_y, hi_x, hi_y, n, radius, tile_rank);
             rc = bin_spots(coords, n, g, tile_rank, s, order, rank, st);
             if (rc) return rc;
@@ -692,13 +884,16 @@ extern "C" __attribute__((visibility("default"))) int fdb_graph_build(const doub
             FDB_CUDA(cudaMemsetAsync(indptr, 0, (n + 1) * 4, st));
             return FDB_OK;
         }
-        rc = run_knn(s, order, n, g, k_eff, nullptr, st);
+        rc = run_knn(s, order, n, g, k_eff, nullptr, st, general);
         if (rc) return rc;
         FDB_CUDA(cudaMemsetAsync(s.extra, 0, (n + 1) * 4, st));
         reverse_count_kernel<<<grid1d(n * k_eff, 256), 256, 0, st>>>(s.knn, n, k_eff, s.extra);
         degree_kernel<<<grid1d(n, 256), 256, 0, st>>>(s.knn, s.extra, n, k_eff, s.deg);
         count_launches(1);
         FDB_LAUNCH_CHECK("degree_kernel");
+    } else if (general) {
+        radius_brute_kernel<false><<<grid1d(n, 128), 128, 0, st>>>(s.pts, n, r2, s.deg, nullptr, nullptr);
+        FDB_LAUNCH_CHECK("radius_brute_kernel<count>");
     } else {
         radius_kernel<false><<<grid1d(n, 128), 128, 0, st>>>(s.xy, n, g, s.tile_rank, s.hist, r2, s.deg, nullptr, nullptr);
         FDB_LAUNCH_CHECK("radius_kernel<count>");
@@ -716,6 +911,8 @@ extern "C" __attribute__((visibility("default"))) int fdb_graph_build(const doub
     if (mode == 0) {
         FDB_CUDA(cudaMemsetAsync(s.cursor, 0, (n + 1) * 4, st));
         knn_fill_kernel<<<grid1d(n, 256), 256, 0, st>>>(s.knn, n, k_eff, indptr, s.cursor, indices);
+    } else if (general) {
+        radius_brute_kernel<true><<<grid1d(n, 128), 128, 0, st>>>(s.pts, n, r2, nullptr, indptr, indices);
     } else {
         radius_kernel<true><<<grid1d(n, 128), 128, 0, st>>>(s.xy, n, g, s.tile_rank, s.hist, r2, nullptr, indptr, indices);
     }
@@ -723,6 +920,15 @@ extern "C" __attribute__((visibility("default"))) int fdb_graph_build(const doub
     count_launches(1);
     FDB_LAUNCH_CHECK("graph fill");
     return FDB_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int fdb_graph_build(const double *coords, int64_t n, int32_t mode, int32_t k, double radius,
+                               int32_t *order, int32_t *rank, int32_t *indptr, int32_t *indices,
+                               int64_t indices_capacity, int64_t *host_nnz, double *host_radius,
+                               void *workspace, int64_t workspace_bytes, void *stream)
+{
+    return fdb_graph_build_nd(coords, n, 2, mode, k, radius, order, rank, indptr, indices, indices_capacity, host_nnz,
+                              host_radius, workspace, workspace_bytes, stream);
 }
 
 extern "C" __attribute__((visibility("default"))) int fdb_graph_to_input_order(const int32_t *indptr, const int32_t *indices, const int32_t *order,

@@ -963,6 +963,41 @@ extern "C" __attribute__((visibility("default"))) int fdb_gene_sums_csr(const in
     return FDB_OK;
 }
 
+// (f3) per-type mean expression of a cells x genes reference (io/loader.py:119-136): float64 sums per (label, gene),
+// warp per cell; the caller divides by the group sizes
+template <typename IndPtr>
+__global__ void __launch_bounds__(256)
+group_sums_kernel(const IndPtr *__restrict__ indptr, const int32_t *__restrict__ indices, const float *__restrict__ values,
+                  const int32_t *__restrict__ labels, int64_t n_rows, int n_genes, double *__restrict__ sums)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = warp_global; row < n_rows; row += n_warps) {
+        const int64_t s = load_ptr(indptr, row), e = load_ptr(indptr, row + 1);
+        const int label = labels[row];
+        if (label < 0) continue;
+        double *out = sums + (int64_t)label * n_genes;
+        for (int64_t j = s + lane; j < e; j += 32) atomicAdd(out + ld_stream(indices + j), (double)ld_stream(values + j));
+    }
+}
+
+extern "C" __attribute__((visibility("default"))) int fdb_group_sums_csr(const void *indptr, int indptr_is_int64, const int32_t *indices,
+                                  const float *values, const int32_t *labels, int64_t n_rows, int32_t n_genes,
+                                  int32_t n_groups, double *sums, void *stream)
+{
+    FDB_REQUIRE(n_rows >= 0 && n_genes >= 0 && n_groups >= 0, "negative shape");
+    if (n_rows == 0) return FDB_OK;
+    FDB_REQUIRE(indptr && labels && sums, "null pointer");
+    const int grid = pick_grid(n_rows, 8, 8);
+    if (indptr_is_int64)
+        group_sums_kernel<int64_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const int64_t *)indptr, indices, values, labels, n_rows, n_genes, sums);
+    else
+        group_sums_kernel<int32_t><<<grid, 256, 0, (cudaStream_t)stream>>>((const int32_t *)indptr, indices, values, labels, n_rows, n_genes, sums);
+    FDB_LAUNCH_CHECK("group_sums_kernel");
+    return FDB_OK;
+}
+
 extern "C" __attribute__((visibility("default"))) int fdb_gene_moments_csr(const void *indptr, int indptr_is_int64, const int32_t *indices,
                                     const float *counts, int64_t n_spots, int32_t n_genes, double *sums,
                                     double *sumsq, void *stream)

@@ -116,6 +116,7 @@ class FlashDeconv:
         self._graph, self._adjacency = res.graph, None
         self.lambda_used_ = res.lambda_used
         self.beta_, self.proportions_, self.info_ = res.beta, res.proportions, res.info
+        self._dominant = res.dominant
         self._fitted = True
         n = max(Y.shape[0], 1)
         say(f"  Average neighbors per spot: {res.graph.nnz / n:.1f}")
@@ -142,7 +143,10 @@ class FlashDeconv:
         return self.beta_
 
     def get_dominant_cell_type(self) -> np.ndarray:
+        """argmax over the cell types, computed on the device with the solve (core/deconv.py:467-478)."""
         self._need_fit()
+        if getattr(self, "_dominant", None) is not None:
+            return self._dominant.astype(np.intp)
         return np.argmax(self.proportions_, axis=1)
 
     def summary(self) -> Dict[str, Any]:

@@ -184,7 +184,7 @@ class DeviceGraph:
 
 
 def build_graph(coords_dev, method="knn", k=6, radius=None) -> DeviceGraph:
-    """coords_dev: float64 CUDA tensor N x 2 (input order)."""
+    """coords_dev: float64 CUDA tensor N x D, D = 1, 2 or 3 (input order; utils/graph.py:15-22)."""
     torch = _native.require_cuda()
     if method not in GRAPH_MODES:
         raise ValueError(f"Unknown method: {method}")
@@ -193,9 +193,9 @@ def build_graph(coords_dev, method="knn", k=6, radius=None) -> DeviceGraph:
     if coords_dev.dim() != 2 or coords_dev.shape[1] == 0:
         raise ValueError("coords must be 2D with at least 1 coordinate dimension, "
                          f"got shape {tuple(coords_dev.shape)}")
-    if coords_dev.shape[1] != 2:
-        raise NotImplementedError("libfdb200 builds 2-D spatial graphs; got coords with "
-                                  f"{coords_dev.shape[1]} columns")
+    dims = int(coords_dev.shape[1])
+    if dims > 3:
+        raise ValueError(f"libfdb200 builds spatial graphs from 1, 2 or 3 coordinates per spot, got {dims}")
     n = int(coords_dev.shape[0])
     dev = coords_dev.device
     coords_dev = coords_dev.contiguous().to(torch.float64)
@@ -209,9 +209,9 @@ def build_graph(coords_dev, method="knn", k=6, radius=None) -> DeviceGraph:
     nnz, rad = C.c_int64(0), C.c_double(0.0)
     for _ in range(3):
         indices = torch.empty(cap, dtype=torch.int32, device=dev)
-        rc = lib.fdb_graph_build(_ptr(coords_dev), n, GRAPH_MODES[method], k_eff, float(radius or 0.0),
-                                 _ptr(order), _ptr(rank), _ptr(indptr), _ptr(indices), cap,
-                                 C.byref(nnz), C.byref(rad), _ptr(ws), ws_bytes, _stream(torch))
+        rc = lib.fdb_graph_build_nd(_ptr(coords_dev), n, dims, GRAPH_MODES[method], k_eff, float(radius or 0.0),
+                                    _ptr(order), _ptr(rank), _ptr(indptr), _ptr(indices), cap,
+                                    C.byref(nnz), C.byref(rad), _ptr(ws), ws_bytes, _stream(torch))
         if rc == -3 and nnz.value > cap:          # radius graphs: degree unknown up front
             cap = int(nnz.value)
             continue
@@ -242,6 +242,7 @@ class SolveResult:
     graph: DeviceGraph
     tables: SketchTables
     timings: dict = field(default_factory=dict)
+    dominant: Optional[np.ndarray] = None      # N int32: argmax over the K types, computed on the device
 
 
 class DevicePath:
@@ -391,10 +392,14 @@ class DevicePath:
             rel = 0.0
         beta_dev = self.current_beta(n_iter)
         obj = self.objective(beta_dev, lam_used, rho_s) if n else 0.0
+        dom = t.empty(max(n, 1), dtype=t.int32, device=self.dev)
+        if n:
+            check(lib.fdb_dominant_type(_ptr(beta_dev), _ptr(self.graph.order), n, self.K, _ptr(dom), _stream(t)),
+                  "dominant_type")
         beta, prop = self.finish(beta_dev, pinned=pinned_out)
         info = dict(converged=conv, n_iterations=n_iter, final_objective=obj,
                     objectives=objectives if verbose else [], final_change=rel)
-        return SolveResult(beta, prop, info, lam_used, self.graph, self.tables)
+        return SolveResult(beta, prop, info, lam_used, self.graph, self.tables, dominant=dom[:n].cpu().numpy())
 
     def _solve_verbose(self, lam, rho_s, max_iter, tol, objectives):
         """Sweep-at-a-time loop used only for verbose=True (objective every 10 sweeps, core/solver.py:399-404)."""
@@ -430,6 +435,20 @@ def gene_moments(csr: DeviceCSR):
                                    _ptr(csr.data), csr.shape[0], G, _ptr(sums), _ptr(sq), _stream(torch)),
           "gene_moments_csr")
     return sums.cpu().numpy(), sq.cpu().numpy()
+
+
+def group_means(csr: DeviceCSR, labels: np.ndarray, n_groups: int) -> np.ndarray:
+    """Mean expression per group of rows of a cells x genes matrix (io/loader.py:119-136) -> host float64
+    (n_groups x G).  labels: int array, one group index per row (negative = skip)."""
+    torch = _native.require_cuda()
+    G = csr.shape[1]
+    lab = np.ascontiguousarray(labels, dtype=np.int32)
+    sums = torch.zeros((n_groups, G), dtype=torch.float64, device=csr.indices.device)
+    lab_d = torch.from_numpy(lab).to(csr.indices.device)
+    check(lib.fdb_group_sums_csr(_ptr(csr.indptr), int(csr.indptr.dtype == torch.int64), _ptr(csr.indices), _ptr(csr.data),
+                                 _ptr(lab_d), csr.shape[0], G, n_groups, _ptr(sums), _stream(torch)), "group_sums_csr")
+    size = np.bincount(lab[lab >= 0], minlength=n_groups).astype(np.float64)
+    return sums.cpu().numpy() / np.maximum(size, 1.0)[:, None]
 
 
 def gene_col_means(csr: DeviceCSR) -> np.ndarray:

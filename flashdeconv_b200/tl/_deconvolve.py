@@ -19,14 +19,18 @@ def _matrix(adata, layer):
 
 
 def _signatures(adata_ref, cell_type_key, layer):
-    """Mean expression per cell type (io/loader.py:119-136)."""
+    """Mean expression per cell type (io/loader.py:119-136).  A sparse cells x genes matrix is reduced on the device
+    (one pass, float64 accumulation); dense references take numpy's grouped mean."""
     M = _matrix(adata_ref, layer)
     labels = np.asarray(adata_ref.obs[cell_type_key])
-    names = np.unique(labels)
+    names, codes = np.unique(labels, return_inverse=True)
+    if sparse.issparse(M) and (M.dtype == np.float32 or np.issubdtype(M.dtype, np.integer)):    # exact in float32
+        from .. import pipeline
+        return pipeline.group_means(pipeline.csr_to_device(M), codes, len(names)), names
+    M = np.asarray(M)
     X = np.zeros((len(names), M.shape[1]), dtype=np.float64)
-    for r, name in enumerate(names):
-        block = M[np.flatnonzero(labels == name)]
-        X[r] = np.asarray(block.mean(axis=0)).ravel()
+    for r in range(len(names)):
+        X[r] = M[codes == r].mean(axis=0)
     return X, names
 
 
@@ -64,11 +68,11 @@ def deconvolve(adata_st: Any, adata_ref: Any, cell_type_key: str = "cell_type", 
     try:
         import pandas as pd
         adata.obsm[key_added] = pd.DataFrame(proportions, index=adata.obs_names, columns=list(names))
-        adata.obs[f"{key_added}_dominant"] = pd.Categorical(np.asarray(names)[np.argmax(proportions, axis=1)],
+        adata.obs[f"{key_added}_dominant"] = pd.Categorical(np.asarray(names)[model.get_dominant_cell_type()],
                                                             categories=list(names))
     except ImportError:                                   # pragma: no cover
         adata.obsm[key_added] = proportions
-        adata.obs[f"{key_added}_dominant"] = np.asarray(names)[np.argmax(proportions, axis=1)]
+        adata.obs[f"{key_added}_dominant"] = np.asarray(names)[model.get_dominant_cell_type()]
     adata.uns[f"{key_added}_params"] = {
         "sketch_dim": sketch_dim, "lambda_spatial": float(model.lambda_used_), "rho_sparsity": rho_sparsity,
         "n_hvg": n_hvg, "n_markers_per_type": n_markers_per_type, "spatial_method": spatial_method,

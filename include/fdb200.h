@@ -119,7 +119,7 @@ int fdb_gene_sums_csr(const int32_t *indices, const float *counts, int64_t nnz, 
  * (:86-133) and build_grid_graph (:136-172): float64 squared distances, k nearest OTHER
  * spots (ties -> smaller original index), union-symmetrised, binary, ascending columns.
  *
- * fdb_graph_build (syncs twice: bounding box, nnz):
+ * fdb_graph_build (syncs: bounding box, cell table upload, nnz; "grid" additionally reads its radius back):
  *   coords        n_spots x 2 float64, input order
  *   mode          0 = kNN with `k`; 1 = radius graph with `radius` (d <= radius);
  *                 2 = "grid": radius = 1.5 * median nearest-neighbour distance
@@ -131,6 +131,13 @@ int fdb_gene_sums_csr(const int32_t *indices, const float *counts, int64_t nnz, 
  * Returns FDB_ERR_WORKSPACE if indices_capacity is too small (host_nnz then holds the need).
  * ------------------------------------------------------------------------------------- */
 int64_t fdb_graph_workspace_bytes(int64_t n_spots, int32_t k);
+/* The same for coords with `dims` = 1, 2 or 3 columns (row-major n_spots x dims) and any k <= 1024.  2-D coordinates
+ * with k <= 32 run the grid-hash kernels; everything else an exhaustive search in float64 (exact, O(n^2): a fallback).
+ * "grid" takes its median on the device (radix select); only the resulting radius crosses PCIe. */
+int fdb_graph_build_nd(const double *coords, int64_t n_spots, int32_t dims, int32_t mode, int32_t k, double radius,
+                       int32_t *order, int32_t *rank, int32_t *indptr, int32_t *indices,
+                       int64_t indices_capacity, int64_t *host_nnz, double *host_radius,
+                       void *workspace, int64_t workspace_bytes, void *stream);
 int fdb_graph_build(const double *coords, int64_t n_spots, int32_t mode, int32_t k, double radius,
                     int32_t *order, int32_t *rank, int32_t *indptr, int32_t *indices,
                     int64_t indices_capacity, int64_t *host_nnz, double *host_radius,
@@ -200,6 +207,18 @@ int fdb_objective_terms(const float *beta, const float *h, const float *ysq, con
  * (core/solver.py:431-452).  Either output may be NULL. */
 int fdb_finish(const float *beta, const int32_t *order, int64_t n_rows, int32_t n_types,
                double *beta_out, double *prop_out, void *stream);
+
+/* (f3) dominant cell type per spot: argmax_k beta[p][k] (first maximum on ties, numpy.argmax), written at
+ * dominant[order[p]] (order may be NULL).  Replaces FlashDeconv.get_dominant_cell_type (core/deconv.py:467-478). */
+int fdb_dominant_type(const float *beta, const int32_t *order, int64_t n_rows, int32_t n_types, int32_t *dominant,
+                      void *stream);
+
+/* (f3) per-group sums of a cells x genes CSR matrix, float64, ACCUMULATED into sums[n_groups x n_genes] (zero it
+ * first); labels[i] < 0 skips cell i.  Divided by the group sizes this is the cell-type signature matrix of
+ * load_reference / prepare_data (io/loader.py:119-136). */
+int fdb_group_sums_csr(const void *indptr, int indptr_is_int64, const int32_t *indices, const float *values,
+                       const int32_t *labels, int64_t n_rows, int32_t n_genes, int32_t n_groups, double *sums,
+                       void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * (f1) gene statistics for HVG selection: per-gene sum and sum of squares of

@@ -244,6 +244,50 @@ def test_knn_vs_oracle_random_points(fo, n, k):
     _assert_same_graph(build_knn_graph(coords, k=k), fo.knn_adjacency(coords, k))
 
 
+@pytest.mark.parametrize("n,dims,k", [(2000, 3, 6), (1500, 1, 4), (3000, 2, 40), (700, 3, 50), (64, 3, 100)])
+def test_knn_general_dimensions_and_large_k(fo, n, dims, k):
+    """utils/graph.py:15-22 takes any number of coordinate columns and any k: 1-D / 3-D coordinates and k > 32 run the
+    exhaustive float64 search; index sets must equal cKDTree's (k >= n clamps to n - 1 like the reference)."""
+    from flashdeconv_b200.graph import build_knn_graph
+    rng = np.random.default_rng(n + k)
+    c = rng.random((n, dims)) * np.array([40.0, 25.0, 6.0])[:dims]
+    _assert_same_graph(build_knn_graph(c, k=k), fo.knn_adjacency(c, k))
+
+
+def test_radius_and_grid_graphs_in_3d(fo):
+    from flashdeconv_b200.graph import build_radius_graph, build_grid_graph
+    rng = np.random.default_rng(8)
+    g = np.stack(np.meshgrid(np.arange(12.0), np.arange(10.0), np.arange(4.0), indexing="ij"), -1).reshape(-1, 3)
+    c = g + rng.normal(0, 0.02, g.shape)
+    _assert_same_graph(build_radius_graph(c, 1.3), fo.radius_adjacency(c, 1.3))
+    _assert_same_graph(build_grid_graph(c), fo.grid_adjacency(c))
+
+
+def test_grid_median_on_device_even_and_odd(fo):
+    """`grid` = radius graph at 1.5 x the median nearest-neighbour distance (utils/graph.py:157-172); the median is a
+    radix select on the device and must be numpy's (mean of the two middle values for an even count)."""
+    from flashdeconv_b200.graph import build_grid_graph
+    rng = np.random.default_rng(2)
+    for n in (1000, 1001, 2, 3, 4097):
+        side = int(np.ceil(np.sqrt(n)))
+        c = (np.stack(np.meshgrid(np.arange(side), np.arange(side)), -1).reshape(-1, 2)[:n] * 3.0
+             + rng.normal(0, 0.4, (n, 2)))
+        _assert_same_graph(build_grid_graph(c), fo.grid_adjacency(c))
+
+
+def test_knn_with_coincident_spots(fo):
+    """Coincident spots (distance 0).  The reference queries k + 1 neighbours and drops the entry whose index equals the
+    row (utils/graph.py:60-74); as long as a spot has fewer than k + 1 exact duplicates its own index is among them and
+    the result is 'the k nearest OTHER spots' -- which is what the device kernel computes (ties at the k-th distance
+    go to the smaller original index, duplicates included).  With k + 1 or more exact duplicates cKDTree's tie order
+    decides whether the row itself is returned; that case is documented as a deviation and not asserted."""
+    from flashdeconv_b200.graph import build_knn_graph
+    rng = np.random.default_rng(12)
+    c = rng.random((600, 2)) * 20
+    c[10] = c[3]; c[11] = c[3]; c[50] = c[49]; c[599] = c[0]          # a triple and two pairs
+    _assert_same_graph(build_knn_graph(c, k=6), fo.knn_adjacency(c, 6))
+
+
 def test_knn_clustered_and_elongated(fo):
     from flashdeconv_b200.graph import build_knn_graph
     rng = np.random.default_rng(3)
@@ -520,6 +564,97 @@ def test_raw_mode_large_abundances_fp16_tile_range(fo):
     X = ds.X / ds.X.sum(axis=1, keepdims=True)
     model, want = _fit_vs_oracle(fo, ds.Y.astype(np.float32), X, ds.coords, preprocess="raw")
     assert float(np.abs(want["beta"]).max()) > 2.0e5 and np.all(np.isfinite(model.beta_))
+
+
+class _Frame(dict):
+    """the slice of pandas.DataFrame / AnnData.obs that tl.deconvolve touches"""
+    def __contains__(self, k):
+        return dict.__contains__(self, k)
+
+
+class _FakeAnnData:
+    """duck-typed AnnData: .X / .layers, .obs, .obs_names, .var_names, .obsm, .uns, .copy()"""
+    def __init__(self, X, var_names, obs=None, obsm=None):
+        self.X, self.layers = X, {}
+        self.var_names = np.asarray(var_names)
+        self.obs_names = np.asarray([f"s{i}" for i in range(X.shape[0])])
+        self.obs = _Frame(obs or {})
+        self.obsm = dict(obsm or {})
+        self.uns = {}
+        self.n_obs = X.shape[0]
+
+    def copy(self):
+        c = _FakeAnnData(self.X.copy(), self.var_names.copy(), dict(self.obs), dict(self.obsm))
+        c.layers = dict(self.layers)
+        return c
+
+
+def test_tl_deconvolve_on_anndata_like_objects(fo):
+    """fd.tl.deconvolve (tl/_deconvolve.py:6-174): gene intersection, signatures = per-type mean of the reference cells
+    (reduced on the device for sparse input), results in .obsm[key] / .obs[key + "_dominant"] / .uns[key + "_params"]
+    with the reference's keys; proportions equal the estimator run on the aligned arrays and the CPU oracle."""
+    import pandas as pd
+    from flashdeconv_b200 import FlashDeconv, tl
+    from flashdeconv_b200.synth import make_dataset
+    ds = make_dataset(n_spots=1500, n_genes=700, n_types=6, depth=800.0, seed=9)
+    rng = np.random.default_rng(1)
+    genes = np.array([f"g{i}" for i in range(700)])
+    # reference cells: 40 noisy cells per type, gene axis permuted and partly disjoint from the spatial one
+    types = np.repeat(np.array(["T%d" % k for k in range(6)]), 40)
+    cells = rng.poisson(np.repeat(ds.X, 40, axis=0) * 3.0).astype(np.float32)
+    perm = rng.permutation(700)[:650]
+    ref = _FakeAnnData(sparse.csr_matrix(cells[:, perm]), genes[perm], obs={"cell_type": types})
+    keep = np.sort(rng.permutation(700)[:660])
+    st = _FakeAnnData(ds.Y[:, keep].tocsr(), genes[keep], obsm={"spatial": ds.coords})
+    ret = tl.deconvolve(st, ref, cell_type_key="cell_type", key_added="fd")
+    assert ret is None
+    P = st.obsm["fd"]
+    assert isinstance(P, pd.DataFrame) and list(P.columns) == ["T%d" % k for k in range(6)] and P.shape == (1500, 6)
+    assert list(st.obs["fd_dominant"].categories) == list(P.columns)
+    assert np.array_equal(np.asarray(st.obs["fd_dominant"]), np.asarray(P.columns)[np.argmax(P.values, axis=1)])
+    want_keys = {"sketch_dim", "lambda_spatial", "rho_sparsity", "n_hvg", "n_markers_per_type", "spatial_method",
+                 "k_neighbors", "radius", "preprocess", "n_genes_used", "n_cell_types", "cell_type_names", "random_state",
+                 "converged", "n_iterations"}
+    assert set(st.uns["fd_params"]) == want_keys and st.uns["fd_params"]["n_cell_types"] == 6
+    # the same numbers from the arrays directly, against the oracle
+    common, i_st, i_ref = np.intersect1d(genes[keep], genes[perm], return_indices=True)
+    Xm = np.stack([cells[types == t][:, perm].astype(np.float64).mean(axis=0) for t in np.unique(types)])[:, i_ref]
+    Ya = ds.Y[:, keep].tocsr()[:, i_st].tocsr()
+    gene_idx, lev = fo.select_genes(Ya.astype(np.float64), Xm, 2000, 50)
+    want = fo.run_path(Ya.astype(np.float64), Xm, ds.coords, gene_idx, lev, d=512, seed=0)
+    check_props(P.values, want["proportions"])
+    assert st.uns["fd_params"]["n_genes_used"] == len(gene_idx)
+    # copy=True leaves the input untouched; missing keys raise like the reference
+    st2 = _FakeAnnData(ds.Y[:, keep].tocsr(), genes[keep], obsm={"spatial": ds.coords})
+    out = tl.deconvolve(st2, ref, copy=True)
+    assert out is not st2 and "flashdeconv" in out.obsm and "flashdeconv" not in st2.obsm
+    with pytest.raises(ValueError, match="Spatial coordinates not found"):
+        tl.deconvolve(_FakeAnnData(ds.Y, genes), ref)
+    with pytest.raises(ValueError, match="Cell type key"):
+        tl.deconvolve(st2, ref, cell_type_key="nope")
+
+
+def test_multiresolution_driver(fo):
+    """f4: bins of 2 x 2 and 4 x 4 base spots; every level is the plain estimator on the aggregated counts."""
+    from flashdeconv_b200 import multires
+    from flashdeconv_b200.synth import make_dataset
+    ds = make_dataset(n_spots=1600, n_genes=500, n_types=5, depth=600.0, jitter=0.0, seed=2)
+    res = multires.run_multiscale_analysis(ds.Y, ds.X, ds.coords, bin_sizes=(8, 16, 32), base_um=8, sketch_dim=128)
+    assert [res[b]["n_spots"] for b in (8, 16, 32)] == [1600, 400, 100]
+    Y16, c16, group = multires.aggregate_to_bin_size(ds.Y, ds.coords, 16, 8)
+    assert Y16.shape == (400, 500) and abs(Y16.sum() - ds.Y.sum()) < 1e-3 and np.bincount(group).tolist() == [4] * 400
+    gene_idx, lev = fo.select_genes(Y16.astype(np.float64), ds.X, 2000, 50)
+    want = fo.run_path(Y16.astype(np.float64), ds.X, c16, gene_idx, lev, d=128, seed=0)
+    check_props(res[16]["proportions"], want["proportions"])
+    for b in (8, 16, 32):
+        assert np.allclose(res[b]["proportions"].sum(1), 1.0) and res[b]["dominant"].shape == (res[b]["n_spots"],)
+
+
+def test_dominant_cell_type_on_device(golden):
+    from flashdeconv_b200 import FlashDeconv
+    m = FlashDeconv(sketch_dim=golden.d, random_state=golden.seed)
+    m.fit(golden.Y, golden.X, golden.coords)
+    assert np.array_equal(m.get_dominant_cell_type(), np.argmax(m.proportions_, axis=1))
 
 
 def _run_tiled(nproc, mode):
