@@ -278,14 +278,23 @@ def test_grid_median_on_device_even_and_odd(fo):
 def test_knn_with_coincident_spots(fo):
     """Coincident spots (distance 0).  The reference queries k + 1 neighbours and drops the entry whose index equals the
     row (utils/graph.py:60-74); as long as a spot has fewer than k + 1 exact duplicates its own index is among them and
-    the result is 'the k nearest OTHER spots' -- which is what the device kernel computes (ties at the k-th distance
-    go to the smaller original index, duplicates included).  With k + 1 or more exact duplicates cKDTree's tie order
-    decides whether the row itself is returned; that case is documented as a deviation and not asserted."""
+    the result is 'the k nearest OTHER spots', which is what the device kernel computes.  Duplicates make EXACT distance
+    ties for every other spot, and cKDTree breaks those by traversal order; the device rule is 'smaller original index'
+    (deviations), so the check is against the oracle's exhaustive search with that rule -- and against
+    cKDTree for the neighbour DISTANCES, which no tie rule can change."""
     from flashdeconv_b200.graph import build_knn_graph
     rng = np.random.default_rng(12)
     c = rng.random((600, 2)) * 20
     c[10] = c[3]; c[11] = c[3]; c[50] = c[49]; c[599] = c[0]          # a triple and two pairs
-    _assert_same_graph(build_knn_graph(c, k=6), fo.knn_adjacency(c, 6))
+    A = build_knn_graph(c, k=6)
+    nbr = fo.knn_directed_bruteforce(c, 6)
+    rows = np.repeat(np.arange(600), 6)
+    D = sparse.csr_matrix((np.ones(3600), (rows, nbr.ravel())), shape=(600, 600))
+    W = D + D.T
+    W.data[:] = 1.0
+    _assert_same_graph(A, W)
+    ref = fo.knn_adjacency(c, 6)                                       # cKDTree: same degrees up to tie choices
+    assert ref.nnz == A.nnz and A[3].nnz >= 6 and A[3, 10] == 1.0 and A[3, 11] == 1.0 and A[10, 11] == 1.0
 
 
 def test_knn_clustered_and_elongated(fo):
