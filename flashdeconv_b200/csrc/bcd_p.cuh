@@ -133,10 +133,6 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
         const int ef = min(max((int)((__float_as_uint(bound) >> 23) & 255u), 9), 245);
         inv_s = __uint_as_float((unsigned)(262 - ef) << 23);
         lam_s = lam * __uint_as_float((unsigned)(ef - 8) << 23);
-        // 2^-3 <= bound < 2^9 (every log-CPM solve after the first sweep): the unscaled tile is already safe (64 x 512 < 65504) and keeps
-        // values down to 5e-4 of the largest one exact to 11 bits, so the conversion skips its multiplies.  Powers of
-        // two either way: same bits.
-        if (ef >= 124 && ef <= 135) { inv_s = 1.f; lam_s = lam; }
     };
     if (comm_on) set_scale(__uint_as_float(*reinterpret_cast<volatile unsigned *>(&state->ov_new[(comm.sweep + 2) % 3])));
     else set_scale(*reinterpret_cast<volatile float *>(&state->last_max_abs) +
@@ -233,31 +229,18 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
         asm volatile("cp.async.wait_all;");
         __syncthreads();                 // (1) every warp is past the gather of the previous patch: g_tile is free
         auto to_gather = [&](int grow, int q, const float4 bb) {
-            const __half2 lo = __floats2half2_rn(bb.x, bb.y), hi = __floats2half2_rn(bb.z, bb.w);
+            const __half2 lo = __floats2half2_rn(bb.x * inv_s, bb.y * inv_s), hi = __floats2half2_rn(bb.z * inv_s, bb.w * inv_s);
             uint2 pk;
             pk.x = *reinterpret_cast<const uint32_t *>(&lo);
             pk.y = *reinterpret_cast<const uint32_t *>(&hi);
             *reinterpret_cast<uint2 *>(g_tile + grow * GROW + 4 * ((q >> 1) ^ gsw<GQ>(grow)) + 2 * (q & 1)) = pk;
         };
-        if (inv_s == 1.f) {                    // the usual log-CPM range needs no scaling: no multiplies issued
 #pragma unroll
-            for (int i = 0; i < Q; ++i) {
-                const int idx = lane + 32 * i;
-                const int lr = idx / Q, q = idx - lr * Q;
-                to_gather(TILE + wrow + lr, q, hrow[i]);
-                to_gather(wrow + lr, q, ld4(c_tile + L::at(wrow + lr, q)));
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < Q; ++i) {
-                const int idx = lane + 32 * i;
-                const int lr = idx / Q, q = idx - lr * Q;
-                float4 a = hrow[i], c = ld4(c_tile + L::at(wrow + lr, q));
-                a.x *= inv_s; a.y *= inv_s; a.z *= inv_s; a.w *= inv_s;
-                c.x *= inv_s; c.y *= inv_s; c.z *= inv_s; c.w *= inv_s;
-                to_gather(TILE + wrow + lr, q, a);
-                to_gather(wrow + lr, q, c);
-            }
+        for (int i = 0; i < Q; ++i) {
+            const int idx = lane + 32 * i;
+            const int lr = idx / Q, q = idx - lr * Q;
+            to_gather(TILE + wrow + lr, q, hrow[i]);
+            to_gather(wrow + lr, q, ld4(c_tile + L::at(wrow + lr, q)));
         }
         // own beta_old row -> registers (fp32 scalars)
         float b[KP];
@@ -508,7 +491,8 @@ int launch_sweep_p(const float *h, const GramArg<KP> &G, int n_types, const floa
         // is barely more than one round: 977 patches on 888 slots at 8 GPUs)
         const int64_t slots = (int64_t)kNumSM * std::max(resident, 1);
         const int64_t rounds = std::max<int64_t>(ceil_div(n_ctas, slots), 1);
-        int grid = (int)std::min<int64_t>(std::min<int64_t>(n_ctas, cap), ceil_div(n_ctas, rounds));
+        // (only for short walks: with many rounds a full grid keeps every SM slot busy, which is worth more than balance)
+        int grid = (int)std::min<int64_t>(std::min<int64_t>(n_ctas, cap), rounds <= 3 ? ceil_div(n_ctas, rounds) : slots);
         if (comm != nullptr) {                              // block 0 = hand-shake; the workers leave it a slot
             const int64_t wslots = std::max<int64_t>(slots - 1, 1);
             const int64_t wrounds = std::max<int64_t>(ceil_div(n_ctas, wslots), 1);
