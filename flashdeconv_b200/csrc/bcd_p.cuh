@@ -50,7 +50,7 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
     uint32_t *g_tile = reinterpret_cast<uint32_t *>(c_tile + TILE * S);           // (TILE + HCAP) x GROW words
     uint8_t *idx_tile = reinterpret_cast<uint8_t *>(g_tile + (TILE + HCAP) * GROW);     // NW x kCodeRounds x 32 byte codes
     int *scal = reinterpret_cast<int *>(idx_tile + NW * kCodeRounds * 32);        // 3 x TILE: row start, end, halo id
-    __shared__ unsigned red[3][NW];
+    __shared__ unsigned red[COMM ? 3 : 2][NW];
     __shared__ int s_flag;
 
     if (*reinterpret_cast<volatile int *>(&state->converged)) return;      // uniform across the grid (and across ranks)
@@ -170,8 +170,10 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
     };
 
     // ---------------- prologue: the first patch's scalars
-    int pi = worker;                                      // position in the processing order
-    int patch = pi < n_patches ? patch_at(pi) : n_patches;
+    // (single GPU: `patch` is the only induction variable, exactly the round-1 loop -- at the 80-register cap one more
+    // live value makes ptxas rematerialise address arithmetic all over the loop body: +4 % instructions, +8 % time)
+    int pi = COMM ? worker : 0;                           // multi-GPU: position in the processing order
+    int patch = COMM ? (pi < n_patches ? patch_at(pi) : n_patches) : (int)blockIdx.x;
     if (patch < n_patches) scalars_async(patch);
     asm volatile("cp.async.commit_group;");
     asm volatile("cp.async.wait_all;");
@@ -179,7 +181,7 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
     float dmax = 0.f, amax = 0.f, nmax = 0.f;
     bool waited = false;
 #pragma unroll 1
-    for (; pi < n_patches; pi += n_workers) {
+    for (; COMM ? pi < n_patches : patch < n_patches;) {
         if (COMM && comm_on && pi >= first_boundary && !waited) {
             // first patch with boundary rows: the hand-shake of the previous sweep has to be complete (peers' rows of
             // that sweep are in the halo slots; its stop test decides whether this sweep exists at all)
@@ -199,7 +201,7 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
             waited = true;
         }
         const int tile_base = patch * TILE;
-        const int next = pi + n_workers < n_patches ? patch_at(pi + n_workers) : n_patches;
+        const int next = COMM ? (pi + n_workers < n_patches ? patch_at(pi + n_workers) : n_patches) : patch + (int)gridDim.x;
         const int my_row = tile_base + own;
         const int my_s = scal[threadIdx.x], my_e = scal[TILE + threadIdx.x];
         const int halo_id = scal[2 * TILE + threadIdx.x];
@@ -416,18 +418,27 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
             // the arrival counter and the last CTA's release, before the flag the peers acquire
             if (pe > __ldg(comm.push_ptr + my_row)) __threadfence_system();
         }
-        patch = next;
+        if (COMM) { patch = next; pi += n_workers; }
+        else patch += gridDim.x;
     }
 
     const unsigned wd = __reduce_max_sync(kFull, __float_as_uint(dmax));
     const unsigned wa = __reduce_max_sync(kFull, __float_as_uint(amax));
     const unsigned wn = COMM ? __reduce_max_sync(kFull, __float_as_uint(nmax)) : 0u;
-    if (lane == 0) { red[0][warp] = wd; red[1][warp] = wa; red[2][warp] = wn; }
+    if (lane == 0) {
+        red[0][warp] = wd;
+        red[1][warp] = wa;
+        if (COMM) red[COMM ? 2 : 0][warp] = wn;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned bd = 0u, ba = 0u, bn = 0u;
 #pragma unroll
-        for (int w = 0; w < NW; ++w) { bd = max(bd, red[0][w]); ba = max(ba, red[1][w]); bn = max(bn, red[2][w]); }
+        for (int w = 0; w < NW; ++w) {
+            bd = max(bd, red[0][w]);
+            ba = max(ba, red[1][w]);
+            if (COMM) bn = max(bn, red[COMM ? 2 : 0][w]);
+        }
         if (comm_on) {
             // overlapped mode: this sweep's norms go to their parity slot; the NEXT launch's hand-shake block closes the sweep
             const int p = comm.sweep & 1;
