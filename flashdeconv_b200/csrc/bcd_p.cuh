@@ -44,7 +44,6 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
     constexpr int Q = L::Q, S = L::S, TILE = NW * 32, HCAP = TILE;
     constexpr int GQ = Q / 2;                            // 16-byte chunks per fp16 gather row
     constexpr int GROW = KP / 2;                         // 32-bit words per gather row
-    constexpr int NP = KP / 2;
     extern __shared__ __align__(16) float sweep_smem[];
     float *c_tile = sweep_smem;                                                   // TILE x S fp32: beta_old, H, beta_new
     uint32_t *g_tile = reinterpret_cast<uint32_t *>(c_tile + TILE * S);           // (TILE + HCAP) x GROW words

@@ -411,10 +411,6 @@ class TiledPath:
         off_ysq = off_h + own_max * self.Kp
         total = off_ysq + ((own_max + 63) // 64) * 64
         key = (total, id(self.group))
-        if __import__("os").environ.get("FDB_PEER_FAKE"):      # timing experiment: ordinary memory, no peers (FDB_PEER_DEBUG=3)
-            if key not in _SYMM_CACHE:
-                buf = t.zeros(total, dtype=t.float32, device=self.dev)
-                _SYMM_CACHE[key] = (buf, None, [buf.data_ptr()] * self.world)
         if key not in _SYMM_CACHE:
             buf = symm_mem.empty(total, dtype=t.float32, device=self.dev)
             buf.zero_()
