@@ -42,6 +42,9 @@ SIGNATURES = {
     "fdb_bcd_finalize": (C.c_int, [_vp, _f32, _vp]),
     "fdb_bcd_solve": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _i32, _f32, _vp, _vp, _vp]),
     "fdb_objective_terms": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
+    "fdb_bcd_solve_wide": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _i32, _f32, _vp, _vp]),
+    "fdb_bcd_sweep_wide": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _f32, _i32, _vp, _vp]),
+    "fdb_objective_terms_wide": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp]),
     "fdb_finish": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "fdb_gene_moments_csr": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "fdb_dominant_type": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp]),

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_obj")
 LIB = os.path.join(HERE, "libfdb200.so")
-SOURCES = ["common.cu", "sketch.cu", "graph.cu", "bcd.cu", "comm.cu", "peer.cu", "tile.cu"]
+SOURCES = ["common.cu", "sketch.cu", "graph.cu", "bcd.cu", "comm.cu", "peer.cu", "tile.cu", "wide.cu"]
 # the production sweep kernel is fully unrolled per row width: one translation unit per Kp, widest (slowest) first
 SWEEP_KP = [64, 56, 48, 40, 32, 24, 16, 8]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

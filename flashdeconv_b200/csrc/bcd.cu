@@ -27,6 +27,10 @@ extern "C" __attribute__((visibility("default"))) int fdb_bcd_init(float *beta, 
 
 namespace fdb {
 
+// any-K form (wide.cu)
+int finish_wide(const float *beta, const int32_t *order, int64_t n_rows, int n_types, double *beta_out, double *prop_out,
+                cudaStream_t st);
+
 // Sweep kernel, tile-cached fp32-gather form (fallback: strong coupling / no plan).  One CTA = NW warps = TILE = 32*NW consecutive spots
 // (tile order => a compact patch of the tissue).
 //   step 1  the CTA streams its TILE beta_old rows and H rows into shared memory with fully
@@ -373,7 +377,8 @@ static int dispatch_sweep(const float *h, const float *host_gram, int n_types, c
         FDB_SWEEP_CASE(40) FDB_SWEEP_CASE(48) FDB_SWEEP_CASE(56) FDB_SWEEP_CASE(64)
 #endif
     default:
-        set_error("n_types must be in [1, %d], got %d", FDB_MAX_TYPES, n_types);
+        set_error("n_types must be in [1, %d] for the register-resident sweep kernels, got %d (use fdb_bcd_solve_wide)", FDB_MAX_TYPES,
+                  n_types);
         return FDB_ERR_UNSUPPORTED;
     }
 #undef FDB_SWEEP_CASE
@@ -672,8 +677,9 @@ extern "C" __attribute__((visibility("default"))) int fdb_finish(const float *be
                           double *beta_out, double *prop_out, void *stream)
 {
     FDB_REQUIRE(n_rows >= 0, "negative n_rows");
-    FDB_REQUIRE(n_types >= 1 && n_types <= FDB_MAX_TYPES, "n_types must be in [1, %d], got %d", FDB_MAX_TYPES, n_types);
+    FDB_REQUIRE(n_types >= 1 && n_types <= FDB_MAX_TYPES_WIDE, "n_types must be in [1, %d], got %d", FDB_MAX_TYPES_WIDE, n_types);
     if (n_rows == 0) return FDB_OK;
+    if (n_types > FDB_MAX_TYPES) return finish_wide(beta, order, n_rows, n_types, beta_out, prop_out, (cudaStream_t)stream);
     const int grid = (int)std::min<int64_t>(ceil_div(n_rows, 8), (int64_t)kNumSM * 16);
     finish_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(beta, order, n_rows, fdb_padded_types(n_types), n_types,
                                                          beta_out, prop_out);
@@ -684,7 +690,7 @@ extern "C" __attribute__((visibility("default"))) int fdb_finish(const float *be
 extern "C" __attribute__((visibility("default"))) int fdb_dominant_type(const float *beta, const int32_t *order, int64_t n_rows, int32_t n_types,
                                  int32_t *dominant, void *stream)
 {
-    FDB_REQUIRE(n_rows >= 0 && n_types >= 1 && n_types <= FDB_MAX_TYPES, "bad shape");
+    FDB_REQUIRE(n_rows >= 0 && n_types >= 1 && n_types <= FDB_MAX_TYPES_WIDE, "bad shape");
     if (n_rows == 0) return FDB_OK;
     FDB_REQUIRE(beta && dominant, "null pointer");
     dominant_kernel<<<(int)ceil_div(n_rows, 256), 256, 0, (cudaStream_t)stream>>>(beta, order, n_rows, fdb_padded_types(n_types),

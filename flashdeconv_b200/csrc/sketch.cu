@@ -673,29 +673,34 @@ sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__re
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 contract_kernel(const float *__restrict__ y_sketch, const float *__restrict__ x_sketch,
-                int64_t n_spots, int d, int n_types, int kp, float *__restrict__ h,
+                int64_t n_spots, int d, int k0, int nk, int n_types, int kp, float *__restrict__ h,
                 float *__restrict__ ysq)
 {
-    extern __shared__ __align__(16) float xs[];     // n_types x d
-    for (int i = threadIdx.x; i < n_types * d; i += blockDim.x) xs[i] = __ldg(x_sketch + i);
+    // one launch handles the type columns [k0, k0 + nk) (nk x d floats of X_s fit in shared memory); the last chunk also
+    // zeroes the padding columns [n_types, kp)
+    extern __shared__ __align__(16) float xs[];     // nk x d
+    for (int i = threadIdx.x; i < nk * d; i += blockDim.x) xs[i] = __ldg(x_sketch + (size_t)k0 * d + i);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int warps_per_cta = blockDim.x >> 5;
+    const int k_end = k0 + nk == n_types ? kp : k0 + nk;
     for (int64_t row = (int64_t)blockIdx.x * warps_per_cta + warp; row < n_spots;
          row += (int64_t)gridDim.x * warps_per_cta) {
         const float *y = y_sketch + row * (int64_t)d;
-        float sq = 0.f;
-        for (int c = lane; c < d; c += 32) {
-            const float v = __ldcs(y + c);
-            sq = fmaf(v, v, sq);
+        if (k0 == 0) {
+            float sq = 0.f;
+            for (int c = lane; c < d; c += 32) {
+                const float v = y[c];
+                sq = fmaf(v, v, sq);
+            }
+            sq = warp_sum(sq);
+            if (lane == 0) ysq[row] = sq;
         }
-        sq = warp_sum(sq);
-        if (lane == 0) ysq[row] = sq;
-        for (int k = 0; k < kp; ++k) {
+        for (int k = k0; k < k_end; ++k) {
             float a = 0.f;
             if (k < n_types)
-                for (int c = lane; c < d; c += 32) a = fmaf(y[c], xs[k * d + c], a);
+                for (int c = lane; c < d; c += 32) a = fmaf(y[c], xs[(k - k0) * d + c], a);
             a = warp_sum(a);
             if (lane == 0) h[row * kp + k] = a;
         }
@@ -794,16 +799,20 @@ extern "C" __attribute__((visibility("default"))) int fdb_sketch_project_csr(
 extern "C" __attribute__((visibility("default"))) int fdb_contract(const float *y_sketch, const float *x_sketch, int64_t n_spots, int32_t d,
                             int32_t n_types, float *h, float *ysq, void *stream)
 {
-    FDB_REQUIRE(n_spots >= 0 && d > 0 && n_types > 0, "bad shape");
+    FDB_REQUIRE(n_spots >= 0 && d > 0 && n_types > 0 && n_types <= FDB_MAX_TYPES_WIDE, "bad shape");
     if (n_spots == 0) return FDB_OK;
-    const size_t smem = (size_t)n_types * d * 4;
-    FDB_REQUIRE(smem <= 200 * 1024, "X_s (%d x %d) does not fit in shared memory", n_types, d);
-    FDB_CUDA(cudaFuncSetAttribute(contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FDB_REQUIRE((size_t)d * 4 <= 200 * 1024, "sketch_dim %d: one row of X_s does not fit in shared memory", d);
     const int kp = fdb_padded_types(n_types);
-    const int grid = pick_grid(n_spots, 8, smem > 100 * 1024 ? 1 : 2);
-    contract_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(y_sketch, x_sketch, n_spots, d, n_types,
-                                                              kp, h, ysq);
-    FDB_LAUNCH_CHECK("contract_kernel");
+    // type columns in chunks whose X_s rows fit in shared memory (one chunk for K <= 100 at d = 512)
+    const int chunk = (int)std::min<size_t>((size_t)n_types, std::max<size_t>(1, (size_t)200 * 1024 / ((size_t)d * 4)));
+    for (int k0 = 0; k0 < n_types; k0 += chunk) {
+        const int nk = std::min(chunk, n_types - k0);
+        const size_t smem = (size_t)nk * d * 4;
+        FDB_CUDA(cudaFuncSetAttribute(contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int grid = pick_grid(n_spots, 8, smem > 100 * 1024 ? 1 : 2);
+        contract_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(y_sketch, x_sketch, n_spots, d, k0, nk, n_types, kp, h, ysq);
+        FDB_LAUNCH_CHECK("contract_kernel");
+    }
     return FDB_OK;
 }
 

@@ -84,9 +84,10 @@ class FlashDeconv:
             raise ValueError(f"Unknown preprocess method: {self.preprocess}. "
                              "Choose from 'log_cpm', 'pearson', or 'raw'.")
         from . import pipeline        # imports the native library: fails loudly when it is missing
-        if X.shape[0] > pipeline.MAX_TYPES:
-            raise ValueError(f"flashdeconv_b200 keeps a spot's abundances in registers and supports at most "
-                             f"{pipeline.MAX_TYPES} cell types; got {X.shape[0]}. Merge rare types or split the reference.")
+        if X.shape[0] > pipeline.MAX_TYPES_WIDE:
+            raise ValueError(f"flashdeconv_b200 supports at most {pipeline.MAX_TYPES_WIDE} cell types "
+                             f"(register-resident kernels up to {pipeline.MAX_TYPES}, warp-per-spot kernels beyond); "
+                             f"got {X.shape[0]}.")
 
         say = print if self.verbose else (lambda *a, **k: None)
         say("FlashDeconv: Starting deconvolution...")

@@ -21,7 +21,8 @@ from . import _native
 from ._native import check, lib
 
 GRAPH_MODES = {"knn": 0, "radius": 1, "grid": 2}
-MAX_TYPES = 64                   # FDB_MAX_TYPES in include/fdb200.h
+MAX_TYPES = 64                   # FDB_MAX_TYPES in include/fdb200.h: register-resident kernels, fused sketch
+MAX_TYPES_WIDE = 1024            # FDB_MAX_TYPES_WIDE: warp-per-spot kernels (csrc/wide.cu), single GPU
 
 
 def _ptr(t):
@@ -252,6 +253,9 @@ class DevicePath:
         self.torch = _native.require_cuda()
         self.csr, self.coords, self.tables, self.K = csr, coords_dev, tables, int(n_types)
         self.Kp = _native.padded_types(self.K)
+        if self.K > MAX_TYPES_WIDE:
+            raise ValueError(f"at most {MAX_TYPES_WIDE} cell types are supported; got {self.K}")
+        self.wide = self.K > MAX_TYPES         # any-K path: unfused sketch + contraction, warp-per-spot sweeps (wide.cu)
         self.dev = csr.indices.device
         t = self.torch
         self.gene_bucket = t.from_numpy(tables.gene_bucket).to(self.dev)
@@ -263,6 +267,10 @@ class DevicePath:
         xst[: tables.d, : self.K] = tables.X_sketch.T
         self.x_sketch_t = t.from_numpy(xst).to(self.dev)
         self.gram32 = np.ascontiguousarray(tables.gram, dtype=np.float32)
+        if self.wide:
+            gp = np.zeros((self.Kp, self.Kp), dtype=np.float32)
+            gp[: self.K, : self.K] = self.gram32
+            self.gram_dev = t.from_numpy(gp).to(self.dev)
         n = csr.shape[0]
         self.h = t.empty((n, self.Kp), dtype=t.float32, device=self.dev)
         self.ysq = t.empty(n, dtype=t.float32, device=self.dev)
@@ -280,11 +288,39 @@ class DevicePath:
         """Fused log-CPM + CountSketch + contraction; rows land in tile order (needs the graph)."""
         c, tb = self.csr, self.tables
         row_map = self.graph.rank if self.graph is not None else None
+        if self.wide:
+            return self._stage_sketch_wide(row_map)
         fn = lib.fdb_sketch_linear_contract_csr if tb.linear else lib.fdb_sketch_contract_csr
         check(fn(_ptr(c.indptr), int(c.indptr.dtype == self.torch.int64), _ptr(c.indices), _ptr(c.data), c.shape[0],
                  c.shape[1], _ptr(self.gene_bucket), _ptr(self.gene_weight), self.d_dev, _ptr(self.x_sketch_t), self.K,
                  _ptr(row_map), _ptr(None), int(len(tb.bucket)), _ptr(self.h), _ptr(self.ysq), _stream(self.torch)),
               "sketch_contract_csr")
+
+    def _stage_sketch_wide(self, row_map, rows_per_pass=262_144):
+        """K > 64: the materialising sketch (fdb_sketch_logcpm_csr / fdb_sketch_project_csr) and the chunked contraction
+        (fdb_contract), a slab of rows at a time so that Y_s never exceeds rows_per_pass x d floats; rows are then placed in
+        tile order."""
+        t, c, tb = self.torch, self.csr, self.tables
+        n = c.shape[0]
+        xs = t.zeros((self.K, self.d_dev), dtype=t.float32, device=self.dev)
+        xs[:, : tb.d] = t.from_numpy(np.ascontiguousarray(tb.X_sketch, dtype=np.float32)).to(self.dev)
+        fn = lib.fdb_sketch_project_csr if tb.linear else lib.fdb_sketch_logcpm_csr
+        is64 = int(c.indptr.dtype == t.int64)
+        ys = t.empty((min(n, rows_per_pass), self.d_dev), dtype=t.float32, device=self.dev)
+        h_in = t.empty((n, self.Kp), dtype=t.float32, device=self.dev) if row_map is not None else self.h
+        q_in = t.empty(n, dtype=t.float32, device=self.dev) if row_map is not None else self.ysq
+        for lo in range(0, n, rows_per_pass):
+            m = min(rows_per_pass, n - lo)
+            ys.zero_()
+            # a row slab of the CSR: the row pointers keep their absolute offsets into indices / data
+            check(fn(_ptr(c.indptr[lo:]), is64, _ptr(c.indices), _ptr(c.data), m, c.shape[1], _ptr(self.gene_bucket),
+                     _ptr(self.gene_weight), self.d_dev, _ptr(ys), _stream(t)), "sketch_rows")
+            check(lib.fdb_contract(_ptr(ys), _ptr(xs), m, self.d_dev, self.K, _ptr(h_in[lo:]), _ptr(q_in[lo:]), _stream(t)),
+                  "contract")
+        if row_map is not None:
+            idx = row_map.to(t.int64)
+            self.h.index_copy_(0, idx, h_in)
+            self.ysq.index_copy_(0, idx, q_in)
 
     def lambda_auto(self, alpha=0.005) -> float:
         """core/spatial.py:181-190 with mean degree = nnz / N."""
@@ -297,6 +333,13 @@ class DevicePath:
 
     def stage_solve(self, lam: float, rho_scaled: float, max_iter: int, tol: float):
         g = self.graph
+        if self.wide:
+            self.plan = None
+            check(lib.fdb_bcd_solve_wide(_ptr(self.h), _ptr(self.gram_dev), _ptr(self.beta_a), _ptr(self.beta_b),
+                                         _ptr(g.indptr), _ptr(g.indices), self.csr.shape[0], self.K, float(lam),
+                                         float(rho_scaled), int(max_iter), float(tol), _ptr(self.state), _stream(self.torch)),
+                  "bcd_solve_wide")
+            return
         self.plan = build_sweep_plan(g.indptr, g.indices, self.csr.shape[0], g.nnz, self.K) if max_iter else None
         check(lib.fdb_bcd_solve(_ptr(self.h), self.gram32.ctypes.data_as(C.c_void_p), _ptr(self.beta_a),
                                 _ptr(self.beta_b), _ptr(g.indptr), _ptr(g.indices), self.csr.shape[0], self.K,
@@ -316,9 +359,14 @@ class DevicePath:
         t = self.torch
         g = self.graph
         out = t.zeros(5, dtype=t.float64, device=self.dev)
-        check(lib.fdb_objective_terms(_ptr(beta_dev), _ptr(self.h), _ptr(self.ysq),
-                                      self.gram32.ctypes.data_as(C.c_void_p), _ptr(g.indptr), _ptr(g.indices),
-                                      self.csr.shape[0], self.K, _ptr(out), _stream(t)), "objective_terms")
+        if self.wide:
+            check(lib.fdb_objective_terms_wide(_ptr(beta_dev), _ptr(self.h), _ptr(self.ysq), _ptr(self.gram_dev),
+                                               _ptr(g.indptr), _ptr(g.indices), self.csr.shape[0], self.K, _ptr(out),
+                                               _stream(t)), "objective_terms_wide")
+        else:
+            check(lib.fdb_objective_terms(_ptr(beta_dev), _ptr(self.h), _ptr(self.ysq),
+                                          self.gram32.ctypes.data_as(C.c_void_p), _ptr(g.indptr), _ptr(g.indices),
+                                          self.csr.shape[0], self.K, _ptr(out), _stream(t)), "objective_terms")
         cross, quad, lap, l1, yty = out.cpu().tolist()
         return 0.5 * (yty - 2.0 * cross + quad) + 0.5 * lam * lap + rho_scaled * l1   # core/solver.py:269-284
 
@@ -405,14 +453,19 @@ class DevicePath:
         """Sweep-at-a-time loop used only for verbose=True (objective every 10 sweeps, core/solver.py:399-404)."""
         g, n = self.graph, self.csr.shape[0]
         st = _stream(self.torch)
-        plan = build_sweep_plan(g.indptr, g.indices, n, g.nnz, self.K)
+        plan = None if self.wide else build_sweep_plan(g.indptr, g.indices, n, g.nnz, self.K)
         check(lib.fdb_bcd_init(_ptr(self.beta_a), n, self.K, _ptr(self.state), st), "bcd_init")
         cur, nxt = self.beta_a, self.beta_b
         n_iter, conv, rel = 0, False, 0.0
         for it in range(max_iter):
-            check(lib.fdb_bcd_sweep(_ptr(self.h), self.gram32.ctypes.data_as(C.c_void_p), _ptr(cur), _ptr(nxt),
-                                    _ptr(g.indptr), _ptr(g.indices), n, self.K, float(lam), float(rho_s),
-                                    float(tol), 1, _ptr(self.state), _ptr(plan), st), "bcd_sweep")
+            if self.wide:
+                check(lib.fdb_bcd_sweep_wide(_ptr(self.h), _ptr(self.gram_dev), _ptr(cur), _ptr(nxt), _ptr(g.indptr),
+                                             _ptr(g.indices), n, self.K, float(lam), float(rho_s), float(tol), 1,
+                                             _ptr(self.state), st), "bcd_sweep_wide")
+            else:
+                check(lib.fdb_bcd_sweep(_ptr(self.h), self.gram32.ctypes.data_as(C.c_void_p), _ptr(cur), _ptr(nxt),
+                                        _ptr(g.indptr), _ptr(g.indices), n, self.K, float(lam), float(rho_s),
+                                        float(tol), 1, _ptr(self.state), _ptr(plan), st), "bcd_sweep")
             n_iter, conv, rel = self.read_state()
             if it % 10 == 0 or it == max_iter - 1:
                 obj = self.objective(nxt, lam, rho_s)

@@ -70,8 +70,39 @@ class _Problem:
         self.a = torch.empty((self.n, self.Kp), dtype=torch.float32, device=dev)
         self.b = torch.empty((self.n, self.Kp), dtype=torch.float32, device=dev)
         self.state = torch.zeros(16, dtype=torch.int32, device=dev)
-        from .pipeline import build_sweep_plan
-        self.plan = build_sweep_plan(self.indptr, self.indices, self.n, Ac.nnz, self.K)
+        from .pipeline import MAX_TYPES, MAX_TYPES_WIDE, build_sweep_plan
+        if self.K > MAX_TYPES_WIDE:
+            raise ValueError(f"at most {MAX_TYPES_WIDE} cell types are supported; got {self.K}")
+        self.wide = self.K > MAX_TYPES             # warp-per-spot kernels (csrc/wide.cu): device Gram, no gather plan
+        if self.wide:
+            gp = np.zeros((self.Kp, self.Kp), dtype=np.float32)
+            gp[: self.K, : self.K] = self.gram32
+            self.gram_dev = torch.from_numpy(gp).to(dev)
+            self.plan = None
+        else:
+            self.plan = build_sweep_plan(self.indptr, self.indices, self.n, Ac.nnz, self.K)
+
+    def solve(self, lam, rho_scaled, max_iter, tol):
+        st = self._stream(self.torch)
+        a = (self._ptr(self.indptr), self._ptr(self.indices), self.n, self.K, float(lam), float(rho_scaled), int(max_iter),
+             float(tol), self._ptr(self.state))
+        if self.wide:
+            self.check(self.lib.fdb_bcd_solve_wide(self._ptr(self.h), self._ptr(self.gram_dev), self._ptr(self.a),
+                                                   self._ptr(self.b), *a, st), "bcd_solve_wide")
+        else:
+            self.check(self.lib.fdb_bcd_solve(self._ptr(self.h), self.gram_ptr, self._ptr(self.a), self._ptr(self.b), *a,
+                                              self._ptr(self.plan), st), "bcd_solve")
+
+    def sweep(self, cur, nxt, lam, rho_scaled, tol):
+        st = self._stream(self.torch)
+        a = (self._ptr(self.indptr), self._ptr(self.indices), self.n, self.K, float(lam), float(rho_scaled), float(tol), 1,
+             self._ptr(self.state))
+        if self.wide:
+            self.check(self.lib.fdb_bcd_sweep_wide(self._ptr(self.h), self._ptr(self.gram_dev), self._ptr(cur), self._ptr(nxt),
+                                                   *a, st), "bcd_sweep_wide")
+        else:
+            self.check(self.lib.fdb_bcd_sweep(self._ptr(self.h), self.gram_ptr, self._ptr(cur), self._ptr(nxt), *a,
+                                              self._ptr(self.plan), st), "bcd_sweep")
 
     def read_state(self):
         st = self.state.cpu()
@@ -79,10 +110,10 @@ class _Problem:
 
     def objective(self, beta_dev, lam, rho_scaled):
         out = self.torch.zeros(5, dtype=self.torch.float64, device="cuda")
-        self.check(self.lib.fdb_objective_terms(self._ptr(beta_dev), self._ptr(self.h), self._ptr(self.ysq),
-                                                self.gram_ptr, self._ptr(self.indptr), self._ptr(self.indices),
-                                                self.n, self.K, self._ptr(out), self._stream(self.torch)),
-                   "objective_terms")
+        fn, gram = (self.lib.fdb_objective_terms_wide, self._ptr(self.gram_dev)) if self.wide else \
+            (self.lib.fdb_objective_terms, self.gram_ptr)
+        self.check(fn(self._ptr(beta_dev), self._ptr(self.h), self._ptr(self.ysq), gram, self._ptr(self.indptr),
+                      self._ptr(self.indices), self.n, self.K, self._ptr(out), self._stream(self.torch)), "objective_terms")
         cross, quad, lap, l1, yty = out.cpu().tolist()
         return 0.5 * (yty - 2.0 * cross + quad) + 0.5 * lam * lap + rho_scaled * l1
 
@@ -99,18 +130,14 @@ def bcd_solve(Y_sketch: np.ndarray, X_sketch: np.ndarray, A, lambda_: float = 0.
     st = P._stream(P.torch)
     objectives = []
     if not verbose:
-        P.check(P.lib.fdb_bcd_solve(P._ptr(P.h), P.gram_ptr, P._ptr(P.a), P._ptr(P.b), P._ptr(P.indptr),
-                                    P._ptr(P.indices), n, K, float(lambda_), float(rho_scaled), int(max_iter),
-                                    float(tol), P._ptr(P.state), P._ptr(P.plan), st), "bcd_solve")
+        P.solve(lambda_, rho_scaled, max_iter, tol)
         n_iter, conv, rel = P.read_state()
     else:
         P.check(P.lib.fdb_bcd_init(P._ptr(P.a), n, K, P._ptr(P.state), st), "bcd_init")
         cur, nxt = P.a, P.b
         n_iter, conv, rel = 0, False, 0.0
         for it in range(max_iter):
-            P.check(P.lib.fdb_bcd_sweep(P._ptr(P.h), P.gram_ptr, P._ptr(cur), P._ptr(nxt), P._ptr(P.indptr),
-                                        P._ptr(P.indices), n, K, float(lambda_), float(rho_scaled), float(tol), 1,
-                                        P._ptr(P.state), P._ptr(P.plan), st), "bcd_sweep")
+            P.sweep(cur, nxt, lambda_, rho_scaled, tol)
             n_iter, conv, rel = P.read_state()
             if it % 10 == 0 or it == max_iter - 1:
                 obj = P.objective(nxt, lambda_, rho_scaled)

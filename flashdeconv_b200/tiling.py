@@ -306,6 +306,9 @@ class TiledPath:
         import torch
         import torch.distributed as dist
         from . import _native, pipeline
+        if int(n_types) > pipeline.MAX_TYPES:
+            raise ValueError(f"the tiled multi-GPU path supports at most {pipeline.MAX_TYPES} cell types (got {int(n_types)}); "
+                             "more types run on one GPU (pipeline.DevicePath, csrc/wide.cu)")
         self.torch, self.dist, self.pl = torch, dist, pipeline
         self.lib, self.check = _native.lib, _native.check
         self.group = group

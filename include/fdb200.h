@@ -41,7 +41,8 @@ typedef enum {
     FDB_ERR_UNSUPPORTED = -4 /* valid request outside what is built    */
 } fdb_status;
 
-#define FDB_MAX_TYPES 64     /* K handled by the register-resident BCD kernels */
+#define FDB_MAX_TYPES 64     /* K handled by the register-resident BCD kernels and the fused sketch */
+#define FDB_MAX_TYPES_WIDE 1024   /* K handled by the warp-per-spot entry points (fdb_*_wide, fdb_contract, fdb_finish) */
 
 int fdb_abi_version(void);
 const char *fdb_last_error(void);
@@ -212,6 +213,25 @@ int fdb_finish(const float *beta, const int32_t *order, int64_t n_rows, int32_t 
  * dominant[order[p]] (order may be NULL).  Replaces FlashDeconv.get_dominant_cell_type (core/deconv.py:467-478). */
 int fdb_dominant_type(const float *beta, const int32_t *order, int64_t n_rows, int32_t n_types, int32_t *dominant,
                       void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Any number of cell types (FDB_MAX_TYPES < K <= FDB_MAX_TYPES_WIDE).  The reference has no limit on K
+ * (core/solver.py:287-428); these entry points restate the same sweep (maintained-residual coordinate
+ * descent, core/solver.py:29-101, Jacobi neighbour sums, :104-184), stop test and objective with one warp
+ * per spot.  gram_dev: DEVICE pointer, Kp x Kp float32 row-major, zero padded, diagonal included (no plan,
+ * no host Gram).  State block, buffer ping-pong and n_iterations protocol as fdb_bcd_solve / fdb_bcd_sweep.
+ * The sketch for such K is fdb_sketch_logcpm_csr / fdb_sketch_project_csr + fdb_contract (any K), the outputs
+ * fdb_finish / fdb_dominant_type (any K).  They also accept K <= FDB_MAX_TYPES (tests compare the two paths).
+ * ------------------------------------------------------------------------------------- */
+int fdb_bcd_solve_wide(const float *h, const float *gram_dev, float *beta_a, float *beta_b,
+                       const int32_t *indptr, const int32_t *indices, int64_t n_rows, int32_t n_types,
+                       float lambda, float rho_scaled, int32_t max_iter, float tol, void *state, void *stream);
+int fdb_bcd_sweep_wide(const float *h, const float *gram_dev, const float *beta_in, float *beta_out,
+                       const int32_t *indptr, const int32_t *indices, int64_t n_rows, int32_t n_types,
+                       float lambda, float rho_scaled, float tol, int32_t finalize, void *state, void *stream);
+int fdb_objective_terms_wide(const float *beta, const float *h, const float *ysq, const float *gram_dev,
+                             const int32_t *indptr, const int32_t *indices, int64_t n_rows,
+                             int32_t n_types, double *out, void *stream);
 
 /* (f3) per-group sums of a cells x genes CSR matrix, float64, ACCUMULATED into sums[n_groups x n_genes] (zero it
  * first); labels[i] < 0 skips cell i.  Divided by the group sizes this is the cell-type signature matrix of

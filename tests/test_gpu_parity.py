@@ -428,6 +428,85 @@ def test_bcd_weak_coupling_all_row_widths_vs_oracle(fo, K, graph):
     assert abs(info["final_objective"] - winfo["final_objective"]) <= 1e-4 * abs(winfo["final_objective"]) + 1e-3
 
 
+@pytest.mark.parametrize("K,graph", [(65, "knn"), (72, "iso"), (100, "knn"), (130, "dense"), (257, "knn")])
+def test_bcd_more_than_64_types_vs_oracle(fo, K, graph):
+    """K > FDB_MAX_TYPES: the warp-per-spot sweep / objective / finish kernels (csrc/wide.cu) and the chunked contraction
+    behind the same solver.bcd_solve call (the reference has no limit on K, core/solver.py:287-428)"""
+    from flashdeconv_b200.solver import bcd_solve, normalize_proportions
+    rng = np.random.default_rng(300 + K)
+    n, d = 600, 160 if K < 200 else 320
+    Xs = rng.standard_normal((K, d)) + 0.3
+    bt = rng.random((n, K)) * (rng.random((n, K)) < 0.1)
+    Ys = bt @ Xs + 0.05 * rng.standard_normal((n, d))
+    coords = rng.random((n, 2))
+    A = {"knn": lambda: fo.knn_adjacency(coords, 6), "iso": lambda: fo.radius_adjacency(coords, 0.03),
+         "dense": lambda: fo.radius_adjacency(coords, 0.15)}[graph]()
+    lam = 2.0 if graph == "iso" else 0.05
+    want, winfo = fo.bcd_solve(Ys, Xs, A, lam, 0.01, 7, 1e-12)
+    got, info = bcd_solve(Ys, Xs, A, lambda_=lam, rho=0.01, max_iter=7, tol=1e-12)
+    assert got.shape == (n, K) and info["n_iterations"] == winfo["n_iterations"] == 7
+    assert np.max(np.abs(got - want)) <= 2e-4 * max(1.0, np.abs(want).max())
+    assert abs(info["final_objective"] - winfo["final_objective"]) <= 1e-4 * abs(winfo["final_objective"]) + 1e-3
+    assert abs(info["final_change"] - winfo["final_change"]) <= 1e-3 * winfo["final_change"] + 1e-6
+    prop = normalize_proportions(got)
+    assert np.allclose(prop, fo.normalize(got), rtol=0, atol=1e-12)
+    # verbose = sweep-at-a-time entry point: same numbers
+    gv, iv = bcd_solve(Ys, Xs, A, lambda_=lam, rho=0.01, max_iter=7, tol=1e-12, verbose=True)
+    assert np.array_equal(gv, got) and len(iv["objectives"]) >= 1
+
+
+def test_wide_kernels_equal_register_kernels_on_a_common_width():
+    """the any-K entry points accept K <= 64 too: same problem through fdb_bcd_solve (fp32-gather kernel, strong coupling)
+    and fdb_bcd_solve_wide; the two descents order their sums differently, nothing else"""
+    import ctypes as C
+    import torch
+    from flashdeconv_b200 import _native
+    from flashdeconv_b200.pipeline import _ptr, _stream
+    from flashdeconv_b200.solver import _Problem
+    rng = np.random.default_rng(9)
+    n, K, d = 900, 40, 96
+    Xs = rng.standard_normal((K, d)) + 0.3
+    Ys = (rng.random((n, K)) * (rng.random((n, K)) < 0.3)) @ Xs + 0.05 * rng.standard_normal((n, d))
+    from scipy.spatial import cKDTree
+    from scipy import sparse
+    coords = rng.random((n, 2))
+    _, nb = cKDTree(coords).query(coords, 5)
+    A = sparse.csr_matrix((np.ones(n * 4), (np.repeat(np.arange(n), 4), nb[:, 1:].ravel())), shape=(n, n))
+    A = ((A + A.T) > 0).astype(np.float64)
+    P = _Problem(Ys, Xs, A)
+    lam, rho = 1.5, 0.02
+    P.solve(lam, rho, 6, 1e-12)
+    n1, _, r1 = P.read_state()
+    ref = (P.a if n1 % 2 == 0 else P.b)[:, :K].cpu().numpy()
+    gp = np.zeros((P.Kp, P.Kp), dtype=np.float32)
+    gp[:K, :K] = P.gram32
+    gd = torch.from_numpy(gp).cuda()
+    a2, b2, st2 = torch.empty_like(P.a), torch.empty_like(P.b), torch.zeros(16, dtype=torch.int32, device="cuda")
+    _native.check(_native.lib.fdb_bcd_solve_wide(_ptr(P.h), _ptr(gd), _ptr(a2), _ptr(b2), _ptr(P.indptr), _ptr(P.indices), n, K,
+                                                 lam, rho, 6, 1e-12, _ptr(st2), _stream(torch)), "bcd_solve_wide")
+    s2 = st2.cpu()
+    assert int(s2[3]) == n1 == 6
+    got = (a2 if n1 % 2 == 0 else b2)[:, :K].cpu().numpy()
+    assert np.max(np.abs(got - ref)) <= 2e-5 * max(1.0, np.abs(ref).max())
+    o1 = P.objective(P.a, lam, rho)
+    out = torch.zeros(5, dtype=torch.float64, device="cuda")
+    _native.check(_native.lib.fdb_objective_terms_wide(_ptr(P.a), _ptr(P.h), _ptr(P.ysq), _ptr(gd), _ptr(P.indptr),
+                                                       _ptr(P.indices), n, K, _ptr(out), _stream(torch)), "objective_wide")
+    cross, quad, lap, l1, yty = out.cpu().tolist()
+    o2 = 0.5 * (yty - 2.0 * cross + quad) + 0.5 * lam * lap + rho * l1
+    assert abs(o1 - o2) <= 1e-6 * abs(o1)
+
+
+def test_fit_transform_with_72_cell_types(fo):
+    """the whole public path with more cell types than the register-resident kernels hold: unfused sketch + chunked
+    contraction, warp-per-spot sweeps, against the oracle with the north-star bars"""
+    from flashdeconv_b200.synth import make_dataset
+    ds = make_dataset(n_spots=1500, n_genes=900, n_types=72, depth=3000.0, jitter=0.1, seed=3)
+    model, want = _fit_vs_oracle(fo, ds.Y, ds.X, ds.coords, sketch_dim=256)
+    assert model.proportions_.shape == (1500, 72)
+    assert np.array_equal(model.get_dominant_cell_type(), np.argmax(model.proportions_, axis=1))
+
+
 def test_bcd_edge_cases():
     from flashdeconv_b200.solver import bcd_solve, normalize_proportions, compute_objective
     from flashdeconv_b200.spatial import compute_laplacian
