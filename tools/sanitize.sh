@@ -13,7 +13,7 @@ from flashdeconv_b200 import pipeline as pl
 from flashdeconv_b200.solver import bcd_solve
 from flashdeconv_b200.graph import build_knn_graph, build_grid_graph, build_radius_graph
 rng = np.random.default_rng(3)
-for n, K in ((3000, 50), (2500, 9), (1000, 17)):
+for n, K in ((3000, 50), (2500, 9), (1000, 17), (600, 100)):
     Xs = rng.standard_normal((K, 64)) + 0.3
     Ys = (rng.random((n, K)) * (rng.random((n, K)) < 0.3)) @ Xs
     A = build_knn_graph(rng.random((n, 2)), k=6)
