@@ -279,7 +279,7 @@ struct SketchScatter {
 // 32-gene word (slot = prefix + popc of the bits below), for wide gene axes / wide rows where the table does not fit
 // next to X_s^T -- the list then carries the gene and the slot is computed for the selected entries only.
 template <typename IndPtr, int NK, bool FIXED, bool TAB>
-__global__ void __launch_bounds__(NK == 1 ? 512 : 448, 1)               // wide rows: 64 accumulator registers per lane
+__global__ void __launch_bounds__(NK == 1 ? 512 : 384, 1)               // wide rows: 64 accumulator registers per lane -> 168 registers, no spills
 sketch_contract_v5_kernel(const IndPtr *__restrict__ indptr, const int32_t *__restrict__ indices,
                           const float *__restrict__ counts, int64_t n_spots, int n_genes, int n_selected,
                           const int32_t *__restrict__ gene_bucket, const float *__restrict__ gene_weight,
@@ -835,7 +835,7 @@ static int launch_fused(const void *indptr, const int32_t *indices, const float 
         const size_t limit = 227 * 1024 - 256;
         auto warps_for = [&](size_t table_bytes) {
             for (int w : {16, 14, 12, 10, 8, 6, 4})
-                if (w * 32 <= (NK == 1 ? 512 : 448) && common + table_bytes + w * per_warp <= limit) return w;
+                if (w * 32 <= (NK == 1 ? 512 : 384) && common + table_bytes + w * per_warp <= limit) return w;
             return 0;
         };
         const size_t tab_bytes = (size_t)(n_genes + 1) * 2, bit_bytes = (size_t)(((n_genes + 31) >> 5) + 1) * 8;
