@@ -273,6 +273,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (inputs are generated on the GPU); there is no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # host side of the end-to-end legs on the GPU's own NUMA node (pinned buffers are first touched there); the CPU legs
+    # below run with the full core set again
+    from flashdeconv_b200 import _native
+    full_affinity = _native.bind_host_to_gpu(local_rank)
     distributed = world > 1
     if distributed:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -401,6 +405,10 @@ def main():
     }
 
     # ---- CPU baseline + parity on a bounded sample of the same workload (rank 0, single GPU) ---------------
+    if full_affinity is not None:
+        out["config"]["host_affinity"] = (f"{len(os.sched_getaffinity(0))} GPU-local cores for the GPU legs (NVML affinity of the "
+                                          f"device), all {len(full_affinity)} for the CPU legs")
+        os.sched_setaffinity(0, full_affinity)
     if not args.no_cpu_baseline and world == 1:
         base, parity = cpu_sample_and_parity(data, cfg, gene_idx, leverage, min(args.cpu_sample, n))
         out["cpu_baseline"], out["parity"] = base, parity

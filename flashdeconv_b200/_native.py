@@ -104,3 +104,33 @@ def require_cuda():
     if not torch.cuda.is_available():
         raise RuntimeError("flashdeconv_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
     return torch
+
+
+def bind_host_to_gpu(device_index: int = 0):
+    """Restricts this process to the CPU cores local to a GPU (NVML's CPU affinity of the device), so that pinned host
+    buffers allocated afterwards live on the GPU's NUMA node and host<->device copies do not cross the socket
+    interconnect (observed: 55 vs 70 GB/s on the same box type).  Returns the previous affinity set (pass it to
+    ``os.sched_setaffinity(0, prev)`` to undo), or None when nothing was changed (no NVML, no such mask, not Linux)."""
+    if os.environ.get("FDB_NO_NUMA_BIND"):
+        return None
+    try:
+        import pynvml
+        torch = require_cuda()
+        props = torch.cuda.get_device_properties(device_index)
+        pynvml.nvmlInit()
+        try:
+            bus = "%08x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        except Exception:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        prev = os.sched_getaffinity(0)
+        want = local & prev
+        if not want or want == prev:
+            return None
+        os.sched_setaffinity(0, want)
+        return prev
+    except Exception:
+        return None
