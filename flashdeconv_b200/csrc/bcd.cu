@@ -288,6 +288,7 @@ __global__ void bcd_finalize_kernel(SolveState *state, float tol)
 __global__ void __launch_bounds__(256)
 bcd_init_kernel(float *__restrict__ beta, int64_t n_rows, int kp, int n_types, SolveState *state)
 {
+    // one 16-byte store per thread (kp is a multiple of 8, so a group of four never straddles two rows)
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0 && state) {
         SolveState z = {};
@@ -295,9 +296,12 @@ bcd_init_kernel(float *__restrict__ beta, int64_t n_rows, int kp, int n_types, S
         z.ov_new[0] = __float_as_uint(z.last_max_abs);                   // the same bound, overlapped multi-GPU mode
         *state = z;
     }
-    if (i >= n_rows * kp) return;
-    const int k = (int)(i % kp);
-    beta[i] = k < n_types ? 1.0f / (float)n_types : 0.f;
+    const int q = kp >> 2;                                               // groups per row
+    if (i >= n_rows * q) return;
+    const int k = 4 * (int)(i % q);
+    const float v = 1.0f / (float)n_types;
+    st4(beta + 4 * i, make_float4(k < n_types ? v : 0.f, k + 1 < n_types ? v : 0.f, k + 2 < n_types ? v : 0.f,
+                                  k + 3 < n_types ? v : 0.f));
 }
 
 // production sweep kernel: defined in bcd_p.cuh, instantiated per row width in bcd_p_inst.cu
@@ -623,7 +627,7 @@ extern "C" __attribute__((visibility("default"))) int fdb_bcd_init(float *beta, 
 {
     FDB_REQUIRE(n_rows >= 0 && n_types >= 1, "bad shape");
     const int kp = fdb_padded_types(n_types);
-    const int64_t total = n_rows * kp;
+    const int64_t total = n_rows * (kp / 4);
     bcd_init_kernel<<<(int)std::max<int64_t>(1, ceil_div(total, 256)), 256, 0, (cudaStream_t)stream>>>(
         beta, n_rows, kp, n_types, (SolveState *)state);
     FDB_LAUNCH_CHECK("bcd_init_kernel");

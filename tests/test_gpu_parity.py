@@ -497,14 +497,47 @@ def test_wide_kernels_equal_register_kernels_on_a_common_width():
     assert abs(o1 - o2) <= 1e-6 * abs(o1)
 
 
-def test_fit_transform_with_72_cell_types(fo):
+@pytest.mark.parametrize("preprocess,method", [("log_cpm", "knn"), ("raw", "radius"), ("pearson", "grid")])
+def test_fit_transform_with_72_cell_types(fo, preprocess, method):
     """the whole public path with more cell types than the register-resident kernels hold: unfused sketch + chunked
-    contraction, warp-per-spot sweeps, against the oracle with the north-star bars"""
+    contraction, warp-per-spot sweeps, against the oracle with the north-star bars; all three preprocess branches and
+    graph kinds"""
+    from flashdeconv_b200 import FlashDeconv
     from flashdeconv_b200.synth import make_dataset
     ds = make_dataset(n_spots=1500, n_genes=900, n_types=72, depth=3000.0, jitter=0.1, seed=3)
-    model, want = _fit_vs_oracle(fo, ds.Y, ds.X, ds.coords, sketch_dim=256)
+    if method == "knn":
+        model, want = _fit_vs_oracle(fo, ds.Y, ds.X, ds.coords, sketch_dim=256, preprocess=preprocess)
+    else:
+        kw = dict(sketch_dim=256, preprocess=preprocess, spatial_method=method, radius=1.6 if method == "radius" else None)
+        model = FlashDeconv(random_state=0, **kw)
+        model.fit(ds.Y, ds.X, ds.coords)
+        Y64 = ds.Y.astype(np.float64)
+        gene_idx, lev = fo.select_genes(Y64, ds.X, 2000, 50)
+        want = fo.run_path(Y64, ds.X, ds.coords, gene_idx, lev, d=256, seed=0, preprocess_method=preprocess, method=method,
+                           radius=kw["radius"])
+        _assert_same_graph(model.adjacency_, want["A"])
+        check_props(model.proportions_, want["proportions"])
+        assert abs(model.info_["final_objective"] - want["info"]["final_objective"]) <= 1e-4 * abs(want["info"]["final_objective"])
     assert model.proportions_.shape == (1500, 72)
     assert np.array_equal(model.get_dominant_cell_type(), np.argmax(model.proportions_, axis=1))
+    assert model.summary()["n_cell_types"] == 72
+
+
+def test_more_than_64_types_edge_cases():
+    """empty problem, zero sweeps and the hard limit on the any-K path"""
+    from flashdeconv_b200 import FlashDeconv
+    from flashdeconv_b200.solver import bcd_solve
+    from flashdeconv_b200.graph import build_knn_graph
+    rng = np.random.default_rng(5)
+    K = 80
+    Xs, Ys = rng.standard_normal((K, 96)), rng.standard_normal((30, 96))
+    A = build_knn_graph(rng.random((30, 2)), k=4)
+    b0, i0 = bcd_solve(Ys, Xs, A, max_iter=0)
+    assert i0["n_iterations"] == 0 and np.allclose(b0, 1.0 / K)
+    be, ie = bcd_solve(np.empty((0, 96)), Xs, sparse.csr_matrix((0, 0)))
+    assert be.shape == (0, K) and ie["converged"] and ie["n_iterations"] == 0
+    with pytest.raises(ValueError, match="at most 1024 cell types"):
+        FlashDeconv().fit(np.ones((4, 2000), dtype=np.float32), np.ones((1025, 2000)), rng.random((4, 2)))
 
 
 def test_bcd_edge_cases():
