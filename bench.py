@@ -376,8 +376,9 @@ def main():
     if not distributed and not args.no_e2e:
         from scipy import sparse
         from flashdeconv_b200 import FlashDeconv
-        Ysp = sparse.csr_matrix((data["host_data"].numpy(), data["host_indices"].numpy(), data["host_indptr"].numpy()),
-                                shape=(n, G))
+        # fresh numpy copies: ordinary pageable memory, as a user's matrix would be (the host_* tensors are pinned)
+        Ysp = sparse.csr_matrix((data["host_data"].numpy().copy(), data["host_indices"].numpy().copy(),
+                                 data["host_indptr"].numpy().copy()), shape=(n, G))
         Xn, cn = data["X"], data["host_coords"].numpy()
         pub = []
         for _ in range(2):

@@ -113,7 +113,7 @@ class FlashDeconv:
                                        spatial_method=self.spatial_method, k_neighbors=self.k_neighbors,
                                        radius=self.radius, max_iter=self.max_iter, tol=self.tol,
                                        random_state=self.random_state, verbose=self.verbose,
-                                       preprocess=self.preprocess)
+                                       preprocess=self.preprocess, pinned_out=True)   # outputs land in page-locked arrays
         self._graph, self._adjacency = res.graph, None
         self.lambda_used_ = res.lambda_used
         self.beta_, self.proportions_, self.info_ = res.beta, res.proportions, res.info
