@@ -79,7 +79,8 @@ def _upload_staged(arr: np.ndarray, torch_dtype, dev, chunk_bytes=64 << 20):
     key = str(dev)
     if key not in _STAGING:
         bufs = [torch.empty(chunk_bytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
-        workers = max(1, min(8, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        workers = max(1, min(int(os.environ.get("FDB_UPLOAD_THREADS", "8")), cores))
         _STAGING[key] = (bufs, ThreadPoolExecutor(max_workers=workers), torch.cuda.Stream(dev), workers)
     bufs, pool, stream, workers = _STAGING[key]
     out = torch.empty(n, dtype=torch_dtype, device=dev)
