@@ -350,7 +350,8 @@ def main():
     def e2e_call():
         if distributed:
             from flashdeconv_b200 import tiling
-            return tiling.deconvolve_path_tiled(host, data["X"], data["host_coords"], gene_idx, leverage, **e2e_kw)
+            return tiling.deconvolve_path_tiled(host, data["X"], data["host_coords"], gene_idx, leverage, download="rank0",
+                                                **e2e_kw)
         return pipeline.deconvolve_path(host, data["X"], data["host_coords"], gene_idx, leverage, **e2e_kw)
 
     e2e_times, res = [], None
@@ -371,7 +372,7 @@ def main():
     e2e = {"value": n / e2e_s if e2e_times else None, "unit": "spots/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s if e2e_times else None,
            "call": "tiling.deconvolve_path_tiled" if distributed else "pipeline.deconvolve_path",
-           "bytes_are": "per rank" if distributed else "total"}
+           "bytes_are": "per rank (upload: 1/N of the rows each; download: rank 0 only)" if distributed else "total"}
     # the estimator call a user makes: scipy CSR in pageable memory, gene selection included (single GPU only)
     if not distributed and not args.no_e2e:
         from scipy import sparse

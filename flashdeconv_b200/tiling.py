@@ -633,14 +633,18 @@ def _host_row_slice(Y, a: int, b: int, dev):
 def deconvolve_path_tiled(Y, X, coords, gene_idx, leverage, *, sketch_dim=512, lambda_spatial="auto",
                           rho_sparsity=0.01, spatial_method="knn", k_neighbors=6, radius=None, max_iter=100,
                           tol=1e-4, random_state=0, pinned_out=False, group=None, preprocess="log_cpm",
-                          y_col_mean=None):
+                          y_col_mean=None, download="all"):
     """Multi-GPU counterpart of pipeline.deconvolve_path: every rank passes the same HOST inputs but uploads only its
     1/R slice of the rows; the fused sketch kernel delivers each H row to the rank that owns its spatial tile (peer
     memory), the ranks solve their tiles with per-sweep halo pushes, and the float64 outputs are all-gathered (own rows)
-    so that every rank returns the full arrays."""
+    so that every rank returns the full arrays.  download="rank0": only rank 0 copies the result to the host (the other
+    ranks return beta = proportions = None and keep nothing but the info dict) -- R downloads of the same 16 K bytes per
+    spot through shared PCIe switches are what dominates the end-to-end time of a multi-GPU call otherwise."""
     import torch
     import torch.distributed as dist
     from . import pipeline
+    if download not in ("all", "rank0"):
+        raise ValueError(f"download must be 'all' or 'rank0', got {download!r}")
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     if preprocess == "pearson" and y_col_mean is None:
         raise ValueError("preprocess='pearson' on several GPUs needs y_col_mean (per-gene means of all spots)")
@@ -662,6 +666,11 @@ def deconvolve_path_tiled(Y, X, coords, gene_idx, leverage, *, sketch_dim=512, l
     b64, p64, info, lam = path.run_resident(method=spatial_method, k=k_neighbors, radius=radius, lam=lambda_spatial,
                                             rho=rho_sparsity, max_iter=max_iter, tol=tol, gather=True)
     path.close()
+    if download == "rank0" and rank != 0:
+        torch.cuda.current_stream().synchronize()
+        res = pipeline.SolveResult(None, None, info, lam, path.graph, tables)
+        res.h2d_bytes, res.d2h_bytes = h2d, 0
+        return res
     if pinned_out:
         hb = torch.empty(b64.shape, dtype=torch.float64, pin_memory=True)
         hp = torch.empty(p64.shape, dtype=torch.float64, pin_memory=True)
