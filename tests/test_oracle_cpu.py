@@ -160,6 +160,16 @@ def test_estimator_validation_messages():
     with pytest.raises(ValueError, match="at least one cell type"):
         m.fit(Y, np.ones((0, 7)), c)
     assert "not fitted" in repr(m)
+    # cell-type limits: 64 on the register-resident kernels, 1024 on the warp-per-spot kernels (checked before any upload)
+    with pytest.raises(ValueError, match="at most 1024 cell types"):
+        m.fit(np.ones((5, 7)), np.ones((1025, 7)), c)
+
+
+def test_multi_gpu_path_rejects_more_than_64_types():
+    """the tiled path keeps the register-resident kernels; the limit is raised before any device work"""
+    from flashdeconv_b200 import tiling
+    with pytest.raises(ValueError, match="at most 64 cell types"):
+        tiling.TiledPath(None, None, None, 65)
 
 
 def test_synth_generator_is_deterministic():
