@@ -180,19 +180,28 @@ def pin_known_answers():
     print("[pin] known answers OK")
 
 
-if __name__ == "__main__":
-    os.makedirs(GOLD, exist_ok=True)
-    pin_known_answers()
-    pin_solver_fixture()
-    pin_path_case("path_sparse_small", n_spots=600, n_genes=900, n_types=6, depth=300.0, d=64, seed=0)
-    pin_path_case("path_dense_small", n_spots=400, n_genes=500, n_types=5, depth=4000.0, d=128, seed=1,
-                  dense=True)
-    pin_path_case("path_sparse_k30", n_spots=2500, n_genes=3000, n_types=30, depth=400.0, d=512, seed=2,
-                  keep_rows=25)
-    pin_path_case("path_grid", n_spots=900, n_genes=700, n_types=8, depth=500.0, d=128, seed=3,
-                  method="grid", jitter=0.0)
+PATH_CASES = {
+    "path_sparse_small": dict(n_spots=600, n_genes=900, n_types=6, depth=300.0, d=64, seed=0),
+    "path_dense_small": dict(n_spots=400, n_genes=500, n_types=5, depth=4000.0, d=128, seed=1, dense=True),
+    "path_sparse_k30": dict(n_spots=2500, n_genes=3000, n_types=30, depth=400.0, d=512, seed=2, keep_rows=25),
+    "path_grid": dict(n_spots=900, n_genes=700, n_types=8, depth=500.0, d=128, seed=3, method="grid", jitter=0.0),
     # the linear preprocess branches (core/deconv.py:199-229), "next" row f2
-    pin_path_case("path_raw", n_spots=500, n_genes=800, n_types=7, depth=300.0, d=64, seed=4, preprocess="raw")
-    pin_path_case("path_pearson", n_spots=700, n_genes=900, n_types=10, depth=350.0, d=128, seed=5,
-                  preprocess="pearson")
+    "path_raw": dict(n_spots=500, n_genes=800, n_types=7, depth=300.0, d=64, seed=4, preprocess="raw"),
+    "path_pearson": dict(n_spots=700, n_genes=900, n_types=10, depth=350.0, d=128, seed=5, preprocess="pearson"),
+    # more cell types than the register-resident kernels hold (warp-per-spot path, csrc/wide.cu); a fixed number of
+    # sweeps so that float32 and float64 cannot stop one sweep apart
+    "path_k72": dict(n_spots=1200, n_genes=900, n_types=72, depth=3000.0, d=256, seed=6, max_iter=30, keep_rows=10),
+}
+
+
+if __name__ == "__main__":
+    # python oracle/pin_against_reference.py [case ...]   (no names: everything)
+    os.makedirs(GOLD, exist_ok=True)
+    only = sys.argv[1:]
+    if not only:
+        pin_known_answers()
+        pin_solver_fixture()
+    for case_name, kw in PATH_CASES.items():
+        if not only or case_name in only:
+            pin_path_case(case_name, **kw)
     print("all pins OK; versions:", VERSIONS)

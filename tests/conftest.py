@@ -57,7 +57,7 @@ class Golden:
         return self.Y.toarray() if self.dense_input else self.Y
 
 
-PATH_CASES = ["path_sparse_small", "path_dense_small", "path_sparse_k30", "path_grid"]
+PATH_CASES = ["path_sparse_small", "path_dense_small", "path_sparse_k30", "path_grid", "path_k72"]   # k72: more types than the register-resident kernels hold
 
 
 LINEAR_CASES = ["path_raw", "path_pearson"]          # preprocess="raw" / "pearson" (core/deconv.py:199-229)
