@@ -11,5 +11,6 @@ __version__ = "0.1.0"
 
 from .estimator import FlashDeconv
 from . import tl
+from . import io
 
 __all__ = ["FlashDeconv", "tl", "__version__"]

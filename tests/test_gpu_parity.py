@@ -755,6 +755,21 @@ def test_tl_deconvolve_on_anndata_like_objects(fo):
         tl.deconvolve(st2, ref, cell_type_key="nope")
 
 
+def test_io_load_reference_sparse_counts_on_device():
+    """io.load_reference on a sparse integer / float32 reference: grouped sums on the device, float64 (io/loader.py:119-136)"""
+    from flashdeconv_b200 import io as fio
+    rng = np.random.default_rng(11)
+    M = sparse.random(700, 300, density=0.1, format="csr", random_state=np.random.RandomState(2),
+                      data_rvs=lambda s: rng.integers(1, 50, s).astype(np.float32))
+    labels = rng.choice(["t%d" % i for i in range(9)], 700)
+    ad = _FakeAnnData(M, [f"g{i}" for i in range(300)], obs={"cell_type": labels})
+    X, names, genes = fio.load_reference(ad)
+    want = np.stack([np.asarray(M[labels == t].mean(axis=0)).ravel() for t in names])
+    assert X.dtype == np.float64 and np.allclose(X, want, rtol=1e-12, atol=0) and len(genes) == 300
+    S = fio.load_reference(ad, method="sum")[0]
+    assert np.allclose(S, np.stack([np.asarray(M[labels == t].sum(axis=0)).ravel() for t in names]), rtol=1e-12)
+
+
 def test_multiresolution_driver(fo):
     """f4: bins of 2 x 2 and 4 x 4 base spots; every level is the plain estimator on the aggregated counts (jittered
     lattice: the aggregated bin centres are tie-free for the k-NN graph)."""

@@ -172,6 +172,61 @@ def test_multi_gpu_path_rejects_more_than_64_types():
         tiling.TiledPath(None, None, None, 65)
 
 
+class _Ad:
+    """the slice of AnnData the io helpers touch"""
+    def __init__(self, X, var, obs=None, obsm=None):
+        import pandas as pd
+        self.X, self.layers, self.var_names = X, {}, np.asarray(var)
+        self.obs, self.obsm, self.uns = pd.DataFrame(obs or {}), dict(obsm or {}), {}
+        self.n_obs = X.shape[0]
+        self.obs_names = np.asarray([f"s{i}" for i in range(X.shape[0])])
+
+
+def test_io_helpers_follow_the_reference_loader():
+    """flashdeconv/io/loader.py:15-318: coordinate lookup order, per-type means, first-occurrence gene alignment in sorted
+    name order, DataFrame + categorical hand-off, error messages (dense inputs: host bookkeeping only)"""
+    from flashdeconv_b200 import io as fio
+    rng = np.random.default_rng(0)
+    st = _Ad(rng.poisson(2.0, (6, 5)).astype(np.float64), ["g3", "g1", "g1", "g7", "g0"], obs={"x": np.arange(6.0), "y": np.ones(6)})
+    Y, coords, genes = fio.load_spatial_data(st)
+    assert Y is st.X and np.array_equal(coords, np.column_stack([np.arange(6.0), np.ones(6)])) and list(genes) == list(st.var_names)
+    st.obsm["X_spatial"] = np.zeros((6, 2))
+    assert np.array_equal(fio.load_spatial_data(st)[1], np.zeros((6, 2)))
+    st.obsm["spatial"] = np.full((6, 2), 3.0)
+    assert np.array_equal(fio.load_spatial_data(st)[1], np.full((6, 2), 3.0))
+    with pytest.raises(ValueError, match="Could not find spatial coordinates"):
+        fio.load_spatial_data(_Ad(st.X, st.var_names))
+    cells = rng.poisson(3.0, (9, 4)).astype(np.float64)
+    labels = np.array(["b", "a", "b", "c", "a", "b", "c", "c", "b"])
+    rf = _Ad(cells, ["g1", "g9", "g0", "g3"], obs={"cell_type": labels})
+    X, names, rgenes = fio.load_reference(rf)
+    assert list(names) == ["a", "b", "c"] and np.allclose(X[1], cells[labels == "b"].mean(0)) and X.dtype == np.float64
+    assert np.allclose(fio.load_reference(rf, method="sum")[0][2], cells[labels == "c"].sum(0))
+    with pytest.raises(ValueError, match="Unknown aggregation method"):
+        fio.load_reference(rf, method="median")
+    with pytest.raises(ValueError, match="Cell type key 'nope' not found"):
+        fio.load_reference(rf, cell_type_key="nope")
+    Ya, Xa, common = fio.align_genes(st.X, X, st.var_names, rgenes)
+    assert list(common) == ["g0", "g1", "g3"]                                   # sorted names
+    assert np.array_equal(Ya, st.X[:, [4, 1, 0]]) and np.array_equal(Xa, X[:, [2, 0, 3]])    # duplicate g1: first occurrence
+    with pytest.raises(ValueError, match="No common genes"):
+        fio.align_genes(st.X, X, np.array(list("abcde")), np.array(list("wxyz")))
+    Yp, Xp, cp, np_names, gp = fio.prepare_data(st, rf)
+    assert np.array_equal(Yp, Ya) and np.array_equal(Xp, Xa) and list(gp) == list(common) and list(np_names) == ["a", "b", "c"]
+    beta = rng.random((6, 3))
+    out = fio.result_to_anndata(beta, st, names)
+    assert out is st and list(st.obsm["flashdeconv"].columns) == ["a", "b", "c"]
+    assert np.array_equal(st.obsm["flashdeconv"].to_numpy(), beta)
+    assert list(st.obs["flashdeconv_dominant"]) == list(names[np.argmax(beta, axis=1)])
+    assert list(fio.result_to_anndata(beta, _Ad(st.X, st.var_names)).obsm["flashdeconv"].columns) == ["CellType_0", "CellType_1", "CellType_2"]
+    with pytest.raises(ValueError, match="beta must be 2D"):
+        fio.result_to_anndata(beta[0], st)
+    with pytest.raises(ValueError, match="beta rows must match"):
+        fio.result_to_anndata(beta[:4], st)
+    with pytest.raises(ValueError, match="must match beta.shape"):
+        fio.result_to_anndata(beta, st, ["a", "b"])
+
+
 def test_synth_generator_is_deterministic():
     from flashdeconv_b200.synth import make_dataset
     a = make_dataset(300, 200, 4, depth=100.0, seed=5)
