@@ -68,7 +68,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(res.stderr)
         return obj
 
-    jobs = [("bcd_p_inst.cu", [f"-DFDB_P_KP={kp}"], f"_{kp}") for kp in SWEEP_KP] + [(s, [], "") for s in SOURCES]
+    # widest rows first: they take longest
+    jobs = [("bcd_p_inst.cu", [f"-DFDB_P_KP={kp}", f"-DFDB_P_COMM={c}"], f"_{kp}_{c}") for kp in sorted(SWEEP_KP, reverse=True)
+            for c in (0, 1)] + [(s, [], "") for s in SOURCES]
     with cf.ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 4)) as ex:
         objs = list(ex.map(one, jobs))
     link = [nvcc, "-shared", *ARCH, "-o", LIB + ".tmp", *objs, "-cudart", "static", "-ldl"]

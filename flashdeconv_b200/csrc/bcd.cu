@@ -305,7 +305,7 @@ bcd_init_kernel(float *__restrict__ beta, int64_t n_rows, int kp, int n_types, S
 }
 
 // production sweep kernel: defined in bcd_p.cuh, instantiated per row width in bcd_p_inst.cu
-template <int KP>
+template <int KP, bool COMM>
 int launch_sweep_p(const float *h, const GramArg<KP> &G, int n_types, const float *beta_in, float *beta_out,
                    const int32_t *indptr, const int32_t *indices, int64_t n_rows, float lam, float rho, float tol,
                    int finalize, SolveState *state, const void *plan, cudaStream_t st, const SweepComm *comm);
@@ -349,8 +349,11 @@ static int launch_sweep(const float *h, const float *host_gram, int n_types, con
     };
     if constexpr (KP % 8 == 0) {
         if (plan != nullptr && variant == 0 && weak_coupling(host_gram, n_types, lam))      // production kernel
-            return launch_sweep_p<KP>(h, G, n_types, beta_in, beta_out, indptr, indices, n_rows, lam, rho, tol,
-                                      finalize, state, plan, st, comm);
+            return comm != nullptr
+                       ? launch_sweep_p<KP, true>(h, G, n_types, beta_in, beta_out, indptr, indices, n_rows, lam, rho, tol,
+                                                  finalize, state, plan, st, comm)
+                       : launch_sweep_p<KP, false>(h, G, n_types, beta_in, beta_out, indptr, indices, n_rows, lam, rho, tol,
+                                                   finalize, state, plan, st, comm);
     }
     if (comm != nullptr) {
         set_error("the fused multi-GPU sweep needs the gather plan and weak coupling");

@@ -1,6 +1,6 @@
 // Production BCD sweep kernel (persistent, software-pipelined, pair-step descent) and its launcher.  One translation
-// unit per row width instantiates launch_sweep_p<KP> (bcd_p_inst.cu, compiled once per FDB_P_KP), so the eight
-// fully unrolled row widths build in parallel; bcd.cu only declares the launcher.
+// unit per (row width, single-/multi-GPU form) instantiates launch_sweep_p<KP, COMM> (bcd_p_inst.cu, compiled once per
+// FDB_P_KP x FDB_P_COMM), so the sixteen fully unrolled forms build in parallel; bcd.cu only declares the launcher.
 #pragma once
 #include "bcd_common.cuh"
 
@@ -460,11 +460,12 @@ bcd_sweep_p_kernel(const float *__restrict__ h, const __grid_constant__ GramPair
 
 
 // host side: Gram operand in pair-row layout, plan view, residency-sized persistent grid
-template <int KP>
+template <int KP, bool COMM>
 int launch_sweep_p(const float *h, const GramArg<KP> &G, int n_types, const float *beta_in, float *beta_out,
                    const int32_t *indptr, const int32_t *indices, int64_t n_rows, float lam, float rho, float tol,
                    int finalize, SolveState *state, const void *plan, cudaStream_t st, const SweepComm *comm)
 {
+    // COMM = (comm != nullptr): the caller picks the instantiation
     // 128-spot patches (4 warps); residency by row width (shared memory): 6 CTAs/SM at 36 KB (Kp <= 32), 4 at 46-54 KB
     // (Kp = 40, 48), 3 at 62-68 KB (Kp = 56, 64)
     constexpr int NWH = 4;
@@ -515,16 +516,10 @@ int launch_sweep_p(const float *h, const GramArg<KP> &G, int n_types, const floa
     };
     // trailing padding columns (Kp - K, rounded down to even) are left out at compile time
     const int pad = KP - n_types;
-    if (comm != nullptr) {
-        if (pad >= 6) return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 6, true>);
-        if (pad >= 4) return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 4, true>);
-        if (pad >= 2) return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 2, true>);
-        return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 0, true>);
-    }
-    if (pad >= 6) return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 6, false>);
-    if (pad >= 4) return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 4, false>);
-    if (pad >= 2) return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 2, false>);
-    return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 0, false>);
+    if (pad >= 6) return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 6, COMM>);
+    if (pad >= 4) return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 4, COMM>);
+    if (pad >= 2) return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 2, COMM>);
+    return run_p(bcd_sweep_p_kernel<KP, NWH, MINB, 0, COMM>);
 }
 
 }  // namespace fdb
