@@ -12,5 +12,6 @@ __version__ = "0.1.0"
 from .estimator import FlashDeconv
 from . import tl
 from . import io
+from . import core, utils          # the reference's sub-package import paths
 
 __all__ = ["FlashDeconv", "tl", "__version__"]

@@ -153,15 +153,8 @@ class SketchTables:
 def countsketch_table(n_genes: int, d: int, leverage, seed):
     """Bucket / sign / weight per selected gene.  numpy's legacy RandomState is called in the
     reference's order (randint, then choice: core/sketching.py:58-59) so draws are bit-identical."""
-    if seed is None or seed is np.random:
-        rng = np.random.mtrand._rand
-    elif isinstance(seed, (int, np.integer)):
-        rng = np.random.RandomState(seed)
-    elif isinstance(seed, np.random.RandomState):
-        rng = seed
-    else:
-        raise ValueError(f"'{seed}' cannot be used to seed a numpy.random.RandomState instance. "
-                         f"Expected None, int, or np.random.RandomState, got {type(seed)}.")
+    from .utils.random import check_random_state
+    rng = check_random_state(seed)
     if leverage is None:
         p = np.full(n_genes, 1.0 / max(n_genes, 1))
     else:

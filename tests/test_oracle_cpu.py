@@ -227,6 +227,35 @@ def test_io_helpers_follow_the_reference_loader():
         fio.result_to_anndata(beta, st, ["a", "b"])
 
 
+def test_reference_import_paths_resolve():
+    """flashdeconv/{core,utils,io,tl}/__init__.py: the names a user of the reference imports resolve under the same
+    sub-package paths (utils.metrics is evaluation code outside the accelerated path and is not provided)"""
+    import importlib
+    import flashdeconv_b200 as fd
+    want = {"core": ["FlashDeconv", "build_countsketch_matrix", "project_to_sketch", "compute_laplacian", "get_neighbor_indices",
+                     "bcd_solve"],
+            "utils": ["select_hvg", "select_markers", "compute_leverage_scores", "build_knn_graph", "build_radius_graph",
+                      "coords_to_adjacency", "check_random_state"],
+            "io": ["load_spatial_data", "load_reference", "align_genes", "result_to_anndata", "prepare_data"],
+            "tl": ["deconvolve"]}
+    for sub, names in want.items():
+        mod = importlib.import_module(f"flashdeconv_b200.{sub}")
+        for name in names:
+            assert callable(getattr(mod, name)), (sub, name)
+    for path, name in (("core.deconv", "FlashDeconv"), ("core.sketching", "sketch_data"), ("core.solver", "normalize_proportions"),
+                       ("core.solver", "compute_objective"), ("core.spatial", "auto_tune_lambda"),
+                       ("utils.genes", "select_informative_genes"), ("utils.graph", "build_grid_graph"),
+                       ("utils.random", "check_random_state"), ("io.loader", "prepare_data")):
+        assert callable(getattr(importlib.import_module(f"flashdeconv_b200.{path}"), name)), (path, name)
+    assert fd.core.FlashDeconv is fd.FlashDeconv
+    from flashdeconv_b200.utils import check_random_state
+    rs = np.random.RandomState(4)
+    assert check_random_state(rs) is rs and check_random_state(None) is np.random.mtrand._rand
+    assert check_random_state(np.int64(7)).randint(0, 100) == np.random.RandomState(7).randint(0, 100)
+    with pytest.raises(ValueError, match="cannot be used to seed"):
+        check_random_state("seed")
+
+
 def test_synth_generator_is_deterministic():
     from flashdeconv_b200.synth import make_dataset
     a = make_dataset(300, 200, 4, depth=100.0, seed=5)
