@@ -170,6 +170,8 @@ def test_multi_gpu_path_rejects_more_than_64_types():
     from flashdeconv_b200 import tiling
     with pytest.raises(ValueError, match="at most 64 cell types"):
         tiling.TiledPath(None, None, None, 65)
+    with pytest.raises(ValueError, match="download must be 'all' or 'rank0'"):
+        tiling.deconvolve_path_tiled(None, None, None, None, None, download="rank1")
 
 
 class _Ad:
